@@ -1,0 +1,730 @@
+// C ABI of libfmcw_cuda (include/fmcw_cuda.h): handle, host-side tables, buffer plumbing.
+// No C++ type or exception crosses the boundary; every entry point returns an fmcw_status.
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fmcw_cuda.h"
+#include "fmcw_internal.cuh"
+
+using namespace fmcw;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- window functions in float64 (MathWorks blackman / chebwin / kaiser restated) ----------------
+std::vector<double> blackman_sym(int N) {
+  std::vector<double> w(N, 1.0);
+  if (N == 1) return w;
+  for (int n = 0; n < N; ++n) {
+    const double t = 2.0 * M_PI * n / (N - 1);
+    w[n] = 0.42 - 0.5 * std::cos(t) + 0.08 * std::cos(2.0 * t);
+  }
+  return w;
+}
+
+std::vector<double> chebwin_sym(int M, double at) {
+  std::vector<double> w(M, 1.0);
+  if (M == 1) return w;
+  const double order = M - 1.0;
+  const double beta = std::cosh(std::acosh(std::pow(10.0, std::fabs(at) / 20.0)) / order);
+  std::vector<std::complex<double>> p(M);
+  for (int k = 0; k < M; ++k) {
+    const double x = beta * std::cos(M_PI * k / M);
+    double v;
+    if (x > 1) v = std::cosh(order * std::acosh(x));
+    else if (x < -1) v = (2 * (M % 2) - 1) * std::cosh(order * std::acosh(-x));
+    else v = std::cos(order * std::acos(x));
+    p[k] = v;
+    if (M % 2 == 0) p[k] *= std::polar(1.0, M_PI / M * k);
+  }
+  std::vector<double> W(M);
+  for (int n = 0; n < M; ++n) {
+    long double acc = 0.0L;
+    for (int k = 0; k < M; ++k) {
+      const long long r = ((long long)n * k) % M;
+      const double ang = -2.0 * M_PI * (double)r / M;
+      acc += (long double)(p[k].real() * std::cos(ang) - p[k].imag() * std::sin(ang));
+    }
+    W[n] = (double)acc;
+  }
+  if (M % 2) {
+    const int n = (M + 1) / 2;
+    int o = 0;
+    for (int i = n - 1; i >= 1; --i) w[o++] = W[i];
+    for (int i = 0; i < n; ++i) w[o++] = W[i];
+  } else {
+    const int n = M / 2 + 1;
+    int o = 0;
+    for (int i = n - 1; i >= 1; --i) w[o++] = W[i];
+    for (int i = 1; i < n; ++i) w[o++] = W[i];
+  }
+  double mx = w[0];
+  for (double v : w) mx = v > mx ? v : mx;
+  for (double& v : w) v /= mx;
+  return w;
+}
+
+double bessel_i0(double x) {
+  const double q = x * x / 4.0;
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 500; ++k) {
+    term *= q / ((double)k * k);
+    sum += term;
+    if (term < 1e-18 * sum) break;
+  }
+  return sum;
+}
+
+std::vector<double> kaiser_sym(int N, double beta) {
+  std::vector<double> w(N, 1.0);
+  if (N == 1) return w;
+  const double alpha = (N - 1) / 2.0, d = bessel_i0(beta);
+  for (int n = 0; n < N; ++n) {
+    const double r = (n - alpha) / alpha;
+    w[n] = bessel_i0(beta * std::sqrt(std::fmax(0.0, 1.0 - r * r))) / d;
+  }
+  return w;
+}
+
+int nextpow2_u64(unsigned long long L) {
+  int lg = 0;
+  while ((1ull << lg) < L) ++lg;
+  return lg;
+}
+
+}  // namespace
+
+struct fmcw_handle {
+  fmcw_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::atomic_flag busy = ATOMIC_FLAG_INIT;
+  std::string err;
+  // chain tables
+  DevBuf win_tab, tw_pair, tw_re, tw_im, dop_tw, dop_win;
+  int bin_lo = 0, bin_hi = -1;
+  // STFT tables
+  StftTables st{};
+  StftGeom geom{};
+  DevBuf plan, bins, kcb, qpos, aq, qend, coef, swin, hard, derr;
+  // scratch
+  DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, xc, det_list, ndet, inten, synth_tab;
+  // state
+  uint64_t n_frames = 0;
+  bool frames_done = false, have_info = false, planned = false;
+  uint64_t n_det_host = 0, halo = 0;
+  uint64_t plan_L = 0, plan_off = 0, plan_avail = 0;
+  StftPlan plan_host{};
+  int n_chunks = 8;
+};
+
+namespace {
+
+struct BusyGuard {
+  fmcw_handle* h; bool ok;
+  explicit BusyGuard(fmcw_handle* hh) : h(hh), ok(!hh->busy.test_and_set(std::memory_order_acquire)) {}
+  ~BusyGuard() { if (ok) h->busy.clear(std::memory_order_release); }
+};
+
+fmcw_status fail(fmcw_handle* h, fmcw_status s, const std::string& msg) {
+  if (h) h->err = msg;
+  return s;
+}
+fmcw_status cuda_fail(fmcw_handle* h, cudaError_t e, const char* what) {
+  cudaGetLastError();
+  const fmcw_status s = (e == cudaErrorMemoryAllocation) ? FMCW_ERR_OOM : FMCW_ERR_CUDA;
+  return fail(h, s, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(call, what)                                          \
+  do {                                                          \
+    cudaError_t _e = (call);                                    \
+    if (_e != cudaSuccess) return cuda_fail(h, _e, what);       \
+  } while (0)
+
+template <class T>
+cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
+  cudaError_t e = b.ensure(v.size() * sizeof(T) + 16);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+fmcw_status validate(const fmcw_config* c, std::string& why) {
+  if (!c) { why = "cfg is NULL"; return FMCW_ERR_POINTER; }
+  if (c->struct_size != sizeof(fmcw_config)) { why = "fmcw_config.struct_size mismatch"; return FMCW_ERR_CONFIG; }
+  if (c->range_fft_size != (uint32_t)NR) { why = "range_fft_size must be 256 (RP:118)"; return FMCW_ERR_CONFIG; }
+  const uint32_t nd = c->Doppler_fft_size;
+  if (nd < 2 || nd > (uint32_t)MAX_ND || (nd & (nd - 1))) { why = "Doppler_fft_size must be a power of two in [2,64]"; return FMCW_ERR_CONFIG; }
+  if (c->max_num_targets != 1) { why = "max_num_targets must be 1 (RP:129)"; return FMCW_ERR_CONFIG; }
+  if (c->num_ADC_samples_per_chirp < 1 || c->num_ADC_samples_per_chirp > 4096) { why = "num_ADC_samples_per_chirp out of [1,4096]"; return FMCW_ERR_CONFIG; }
+  if (c->num_chirps_per_frame < 1 || c->num_chirps_per_frame > 4096) { why = "num_chirps_per_frame out of [1,4096]"; return FMCW_ERR_CONFIG; }
+  if (c->num_Rx_antennas < 1 || c->rx_select >= c->num_Rx_antennas) { why = "rx_select out of range"; return FMCW_ERR_CONFIG; }
+  if (c->window_length < 2 || c->window_length > 1024) { why = "window_length out of [2,1024]"; return FMCW_ERR_CONFIG; }
+  if (c->overlap >= c->window_length) { why = "overlap must be < window_length (RP:179)"; return FMCW_ERR_CONFIG; }
+  if (c->MAX_FREQ_BINS < 2 || c->MAX_FREQ_BINS > (uint32_t)MAX_NQ) { why = "MAX_FREQ_BINS out of [2,1024]"; return FMCW_ERR_CONFIG; }
+  if (c->peak_mode > 1) { why = "peak_mode"; return FMCW_ERR_CONFIG; }
+  if (!(c->PRT > 0) || !(c->adc_scale > 0) || !(c->dist_per_bin > 0)) { why = "PRT, adc_scale and dist_per_bin must be positive"; return FMCW_ERR_CONFIG; }
+  return FMCW_OK;
+}
+
+void fill_tables(fmcw_handle* h) {
+  h->st.plan = h->plan.as<StftPlan>();
+  h->st.bins = h->bins.as<int>();
+  h->st.kcb = h->kcb.as<float>();
+  h->st.qpos = h->qpos.as<int>();
+  h->st.aq = h->aq.as<float>();
+  h->st.qend = h->qend.as<int>();
+  h->st.coef = h->coef.as<float>();
+  h->st.win = h->swin.as<float>();
+  h->st.hard_list = h->hard.as<unsigned int>();
+}
+
+fmcw_status read_info(fmcw_handle* h) {
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  unsigned long long nd = 0;
+  if (h->frames_done) CK(cudaMemcpy(&nd, h->ndet.p, sizeof(nd), cudaMemcpyDeviceToHost), "read n_det");
+  h->n_det_host = nd;
+  CK(cudaMemcpy(&h->plan_host, h->plan.p, sizeof(StftPlan), cudaMemcpyDeviceToHost), "read plan");
+  int derr = 0;
+  CK(cudaMemcpy(&derr, h->derr.p, sizeof(int), cudaMemcpyDeviceToHost), "read device status");
+  h->have_info = true;
+  if (derr != 0) {
+    int zero = 0;
+    cudaMemcpy(h->derr.p, &zero, sizeof(int), cudaMemcpyHostToDevice);
+    const char* why = derr == -2 ? "more DTFT bins than the plan tables hold" :
+                      derr == -3 ? "a query chunk exceeds the shared-memory bin budget" :
+                      derr == -4 ? "intensity capacity_cols is smaller than the column count" :
+                      derr == -5 ? "too many columns need the exhaustive max search" : "device-side failure";
+    return fail(h, derr == -4 ? FMCW_ERR_SIZE : FMCW_ERR_CUDA, why);
+  }
+  return FMCW_OK;
+}
+
+// frames -> device buffers (internal or caller's), compaction; no synchronisation
+struct FrameDev { float* rmax; int32_t* det; int32_t* rbin; float* rmag; int32_t* dbin; float2* drow; float* slow; };
+
+fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const fmcw_frame_out* out, FrameDev& d,
+                       bool& any_host) {
+  const fmcw_config& c = h->cfg;
+  const uint32_t NTS = c.num_ADC_samples_per_chirp, PN = c.num_chirps_per_frame, ND = c.Doppler_fft_size;
+  if (!iq && n_frames) return fail(h, FMCW_ERR_POINTER, "iq is NULL");
+  any_host = false;
+  const size_t rx_words = (size_t)PN * NTS;           // uint32 words per (frame, rx)
+  uint32_t n_rx = c.num_Rx_antennas, rx_sel = c.rx_select;
+  const uint32_t* d_iq = reinterpret_cast<const uint32_t*>(iq);
+  if (n_frames && !is_device_ptr(iq)) {
+    any_host = true;
+    CK(h->iq_stage.ensure(n_frames * rx_words * 4), "alloc iq staging");
+    // only the selected RX crosses PCIe (the reference ignores the other antennas, RP:202)
+    CK(cudaMemcpy2DAsync(h->iq_stage.p, rx_words * 4, reinterpret_cast<const uint32_t*>(iq) + (size_t)rx_sel * rx_words,
+                         (size_t)n_rx * rx_words * 4, rx_words * 4, n_frames, cudaMemcpyHostToDevice, h->stream),
+       "H2D iq");
+    d_iq = h->iq_stage.as<uint32_t>();
+    n_rx = 1; rx_sel = 0;
+  }
+  auto pick = [&](void* user, DevBuf& b, size_t bytes, bool needed, void*& dst) -> cudaError_t {
+    dst = nullptr;
+    if (user && is_device_ptr(user)) { dst = user; return cudaSuccess; }
+    if (user) any_host = true;
+    if (!user && !needed) return cudaSuccess;
+    cudaError_t e = b.ensure(bytes ? bytes : 16);
+    dst = b.p;
+    return e;
+  };
+  const size_t nf = n_frames ? n_frames : 1;
+  void* t;
+  CK(pick(out ? out->range_max_abs : nullptr, h->o_rmax, nf * NR * 4, false, t), "alloc"); d.rmax = (float*)t;
+  CK(pick(out ? out->detected : nullptr, h->o_det, nf * 4, true, t), "alloc"); d.det = (int32_t*)t;
+  CK(pick(out ? out->range_bin : nullptr, h->o_rbin, nf * 4, false, t), "alloc"); d.rbin = (int32_t*)t;
+  CK(pick(out ? out->range_mag : nullptr, h->o_rmag, nf * 4, false, t), "alloc"); d.rmag = (float*)t;
+  CK(pick(out ? out->doppler_bin : nullptr, h->o_dbin, nf * 4, false, t), "alloc"); d.dbin = (int32_t*)t;
+  CK(pick(out ? out->doppler_row : nullptr, h->o_drow, nf * ND * 8, false, t), "alloc"); d.drow = (float2*)t;
+  CK(pick(out ? out->slow_time_mag : nullptr, h->o_slow, nf * PN * 4, true, t), "alloc"); d.slow = (float*)t;
+  CK(h->det_list.ensure(nf * 4), "alloc det_list");
+  CK(h->xc.ensure((nf * PN + c.window_length) * 4), "alloc slow-time signal");
+
+  ChainParams p{};
+  p.iq = d_iq; p.n_frames = n_frames; p.NTS = NTS; p.PN = PN; p.n_rx = n_rx; p.rx_sel = rx_sel; p.ND = ND;
+  p.nts_fft = NTS < (uint32_t)NR ? NTS : (uint32_t)NR;
+  p.win_tab = h->win_tab.as<float4>(); p.tw_pair = h->tw_pair.as<float2>();
+  p.tw_re = h->tw_re.as<float>(); p.tw_im = h->tw_im.as<float>();
+  p.dop_tw = h->dop_tw.as<float2>(); p.dop_win = h->dop_win.as<float>();
+  p.bin_lo = h->bin_lo; p.bin_hi = h->bin_hi;
+  p.range_thr = (float)c.range_threshold; p.dop_thr = (float)c.Doppler_threshold; p.peak_mode = (int)c.peak_mode;
+  p.range_max_abs = d.rmax; p.detected = d.det; p.range_bin = d.rbin; p.range_mag = d.rmag;
+  p.doppler_bin = d.dbin; p.doppler_row = d.drow; p.slow_mag = d.slow;
+  p.spec_out = nullptr;
+  CK(launch_frame_chain(p, h->stream), "frame chain kernel");
+  CompactParams cp{d.det, n_frames, PN, d.slow, h->xc.as<float>(), h->det_list.as<uint32_t>(), h->ndet.as<unsigned long long>()};
+  CK(launch_compact(cp, h->stream), "compaction kernels");
+  h->n_frames = n_frames; h->frames_done = true; h->have_info = false; h->planned = false; h->halo = 0;
+  return FMCW_OK;
+}
+
+fmcw_status copy_frame_outputs(fmcw_handle* h, uint64_t n, const fmcw_frame_out* out, const FrameDev& d) {
+  if (!out || !n) return FMCW_OK;
+  const fmcw_config& c = h->cfg;
+  auto back = [&](void* user, const void* dev, size_t bytes) -> cudaError_t {
+    if (!user || user == dev || is_device_ptr(user)) return cudaSuccess;
+    return cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, h->stream);
+  };
+  CK(back(out->range_max_abs, d.rmax, n * NR * 4), "D2H range_max_abs");
+  CK(back(out->detected, d.det, n * 4), "D2H detected");
+  CK(back(out->range_bin, d.rbin, n * 4), "D2H range_bin");
+  CK(back(out->range_mag, d.rmag, n * 4), "D2H range_mag");
+  CK(back(out->doppler_bin, d.dbin, n * 4), "D2H doppler_bin");
+  CK(back(out->doppler_row, d.drow, n * c.Doppler_fft_size * 8), "D2H doppler_row");
+  CK(back(out->slow_time_mag, d.slow, n * c.num_chirps_per_frame * 4), "D2H slow_time_mag");
+  return FMCW_OK;
+}
+
+// plan (+ max) + main on the signal held in h->xc.  d_ndet != null: sizes come from the device.
+fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, uint64_t offset, uint64_t L_local,
+                     uint64_t L_avail, bool compute_max, double pmax_override, const fmcw_stft_out* sout,
+                     uint64_t cols_upper) {
+  if (!sout || !sout->intensity) return fail(h, FMCW_ERR_POINTER, "stft output buffer is NULL");
+  if (sout->layout > 1) return fail(h, FMCW_ERR_CONFIG, "unknown intensity layout");
+  const uint32_t nq = h->cfg.MAX_FREQ_BINS;
+  const bool dev_out = is_device_ptr(sout->intensity);
+  uint64_t cap = sout->capacity_cols;
+  uint64_t ld = sout->ld_cols ? sout->ld_cols : sout->capacity_cols;
+  if (sout->layout == FMCW_LAYOUT_FREQ_MAJOR && ld < cap) return fail(h, FMCW_ERR_SIZE, "ld_cols < capacity_cols");
+  float* d_out = sout->intensity;
+  uint64_t d_ld = ld;
+  if (!dev_out) {
+    const uint64_t need = cols_upper < cap ? cols_upper : cap;     // columns the staging buffer must hold
+    CK(h->inten.ensure((size_t)(need ? need : 1) * nq * 4), "alloc intensity staging");
+    d_out = h->inten.as<float>();
+    cap = need; d_ld = need;
+  }
+  if (!h->planned) {
+    CK(launch_stft_plan(h->st, h->geom, from_device_count ? h->ndet.as<unsigned long long>() : nullptr,
+                        h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks, h->stream),
+       "stft plan kernel");
+    h->planned = true; h->plan_L = L_total; h->plan_off = offset; h->plan_avail = L_avail;
+    if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream), "stft max kernels");
+  }
+  if (!compute_max) CK(launch_stft_set_max(h->st, pmax_override, h->stream), "stft set max");
+  CK(launch_stft_main(h->st, h->geom, h->xc.as<float>(), d_out, cap, d_ld, (int)sout->layout, h->derr.as<int>(), h->stream),
+     "stft main kernel");
+  h->have_info = false;
+  if (!dev_out) {
+    fmcw_status s = read_info(h);
+    if (s != FMCW_OK) return s;
+    const uint64_t ncl = h->plan_host.valid > 0 ? h->plan_host.col_end - h->plan_host.col_begin : 0;
+    if (ncl > sout->capacity_cols) return fail(h, FMCW_ERR_SIZE, "intensity capacity_cols is smaller than the column count");
+    if (ncl) {
+      if (sout->layout == FMCW_LAYOUT_TIME_MAJOR)
+        CK(cudaMemcpyAsync(sout->intensity, d_out, (size_t)ncl * nq * 4, cudaMemcpyDeviceToHost, h->stream), "D2H intensity");
+      else
+        CK(cudaMemcpy2DAsync(sout->intensity, ld * 4, d_out, d_ld * 4, ncl * 4, nq, cudaMemcpyDeviceToHost, h->stream),
+           "D2H intensity");
+    }
+    CK(cudaStreamSynchronize(h->stream), "synchronize");
+  }
+  return FMCW_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* fmcw_version(void) { return "libfmcw_cuda 0.1.0 (sm_100a)"; }
+
+const char* fmcw_status_string(fmcw_status s) {
+  switch (s) {
+    case FMCW_OK: return "ok";
+    case FMCW_ERR_CONFIG: return "bad configuration";
+    case FMCW_ERR_POINTER: return "bad pointer";
+    case FMCW_ERR_CUDA: return "CUDA error";
+    case FMCW_ERR_NCCL: return "NCCL error";
+    case FMCW_ERR_OOM: return "out of memory";
+    case FMCW_ERR_BUSY: return "handle busy";
+    case FMCW_ERR_SIZE: return "bad size";
+    case FMCW_ERR_NO_DATA: return "not enough slow-time samples";
+    case FMCW_ERR_STATE: return "call order violated";
+  }
+  return "unknown";
+}
+
+fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64_t calib_len, int device,
+                        fmcw_handle** out) {
+  if (!out) return FMCW_ERR_POINTER;
+  *out = nullptr;
+  std::string why;
+  fmcw_status vs = validate(cfg, why);
+  if (vs != FMCW_OK) return vs;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return FMCW_ERR_CUDA; }   // no CPU fallback
+  if (device < 0 || device >= ndev) return FMCW_ERR_CONFIG;
+  fmcw_handle* h = new (std::nothrow) fmcw_handle();
+  if (!h) return FMCW_ERR_OOM;
+  h->cfg = *cfg;
+  h->device = device;
+  const fmcw_config& c = h->cfg;
+  const uint32_t NTS = c.num_ADC_samples_per_chirp, PN = c.num_chirps_per_frame, ND = c.Doppler_fft_size;
+  fmcw_status rc = FMCW_OK;
+  auto bail = [&](fmcw_status s) { fmcw_destroy(h); return s; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(FMCW_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FMCW_ERR_CUDA);
+
+  // ---- calibration (RP:167-174), window (RP:138) and scale (RP:121, 203) folded into one table ----
+  std::vector<std::complex<double>> cal(NTS, {0.0, 0.0});
+  if (calib_data && calib_len) {
+    const uint64_t N_cal = calib_len / (2ull * c.num_Rx_antennas);
+    const uint64_t dec = N_cal / NTS;
+    if (dec == 0 || N_cal * 2ull * c.num_Rx_antennas != calib_len) return bail(FMCW_ERR_SIZE);
+    const uint64_t base = 2ull * c.rx_select * N_cal;
+    for (uint32_t n = 0; n < NTS && (uint64_t)n * dec < N_cal; ++n)
+      cal[n] = {calib_data[base + (uint64_t)n * dec], calib_data[base + N_cal + (uint64_t)n * dec]};
+  }
+  std::complex<double> cmean(0.0, 0.0);
+  for (auto& v : cal) cmean += v;
+  cmean /= (double)NTS;
+  const std::vector<double> wr = blackman_sym((int)NTS);
+  const uint32_t nts_fft = NTS < (uint32_t)NR ? NTS : (uint32_t)NR;
+  std::vector<float4> wt(NR, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (uint32_t n = 0; n < nts_fft; ++n) {
+    const double w2 = 2.0 * wr[n];
+    const std::complex<double> hh = w2 * c.IF_scale * (cal[n] - cmean);
+    wt[n] = make_float4((float)(w2 * c.IF_scale / (c.adc_scale * (double)NTS)), (float)hh.real(), (float)hh.imag(), 0.f);
+  }
+  std::vector<float2> twp(256);
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int s = 0; s < 16; ++s) {
+      const double a = -2.0 * M_PI * (double)(s * k1) / NR;
+      twp[k1 * 16 + s] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+  std::vector<float> twre(272, 0.f), twim(272, 0.f);
+  for (int k = 0; k < NR; ++k) {
+    const double a = -2.0 * M_PI * (double)k / NR;
+    twre[k + (k >> 4)] = (float)std::cos(a);
+    twim[k + (k >> 4)] = (float)std::sin(a);
+  }
+  std::vector<float2> dtw(ND);
+  for (uint32_t k = 0; k < ND; ++k) {
+    const double a = -2.0 * M_PI * (double)k / ND;
+    dtw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  const std::vector<double> wd = chebwin_sym((int)PN, 100.0);
+  std::vector<float> dwin(ND, 0.f);
+  for (uint32_t i = 0; i < ND && i < PN; ++i) dwin[i] = (float)(2.0 * wd[i]);
+  // range gate of f_search_peak: (n-1)*dist_per_bin in [min_distance, max_distance], n = 3..len-2
+  h->bin_lo = NR; h->bin_hi = -1;
+  for (int n = 3; n <= NR - 2; ++n) {
+    const double r = (double)(n - 1) * c.dist_per_bin;
+    if (r >= c.min_distance && r <= c.max_distance) { if (n - 1 < h->bin_lo) h->bin_lo = n - 1; h->bin_hi = n - 1; }
+  }
+  const std::vector<double> wk = kaiser_sym((int)c.window_length, c.kaiser_beta);
+  std::vector<float> swin(wk.begin(), wk.end());
+
+  h->geom.win = c.window_length; h->geom.hop = c.window_length - c.overlap; h->geom.nq = c.MAX_FREQ_BINS;
+  h->geom.fs = 1.0 / c.PRT;
+  const int nb_max = 2 * (int)c.MAX_FREQ_BINS + 2;
+  const int half = (int)c.window_length / 2;
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  ok(upload(h->win_tab, wt, h->stream)); ok(upload(h->tw_pair, twp, h->stream));
+  ok(upload(h->tw_re, twre, h->stream)); ok(upload(h->tw_im, twim, h->stream));
+  ok(upload(h->dop_tw, dtw, h->stream)); ok(upload(h->dop_win, dwin, h->stream));
+  ok(upload(h->swin, swin, h->stream));
+  ok(h->plan.ensure(sizeof(StftPlan))); ok(h->bins.ensure((size_t)nb_max * 4)); ok(h->kcb.ensure((size_t)nb_max * 4));
+  ok(h->qpos.ensure(MAX_NQ * 4)); ok(h->aq.ensure(MAX_NQ * 4)); ok(h->qend.ensure((size_t)(nb_max + 2) * 4));
+  ok(h->coef.ensure((size_t)nb_max * 2 * half * 4 + 64));
+  h->st.hard_cap = 1u << 20;
+  ok(h->hard.ensure((size_t)h->st.hard_cap * 4));
+  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16));
+  if (e == cudaSuccess) {
+    ok(cudaMemsetAsync(h->plan.p, 0, sizeof(StftPlan), h->stream));
+    ok(cudaMemsetAsync(h->derr.p, 0, 16, h->stream));
+    ok(cudaMemsetAsync(h->ndet.p, 0, 16, h->stream));
+    ok(cudaStreamSynchronize(h->stream));
+  }
+  if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? FMCW_ERR_OOM : FMCW_ERR_CUDA; cudaGetLastError(); return bail(rc); }
+  h->st.nb_max = nb_max;
+  fill_tables(h);
+  *out = h;
+  return FMCW_OK;
+}
+
+void fmcw_destroy(fmcw_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb,
+                   &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
+                   &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->xc, &h->det_list, &h->ndet, &h->inten,
+                   &h->synth_tab};
+  for (DevBuf* b : all) b->release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* fmcw_last_error(const fmcw_handle* h) { return h ? h->err.c_str() : "NULL handle"; }
+void* fmcw_get_stream(fmcw_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+fmcw_status fmcw_synchronize(fmcw_handle* h) {
+  if (!h) return FMCW_ERR_POINTER;
+  cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_get_info(fmcw_handle* h, fmcw_run_info* info) {
+  if (!h || !info) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  fmcw_status s = read_info(h);
+  if (s != FMCW_OK) return s;
+  const StftPlan& P = h->plan_host;
+  std::memset(info, 0, sizeof(*info));
+  info->n_frames = h->n_frames;
+  info->n_detected = h->n_det_host;
+  info->L_local = h->n_det_host * h->cfg.num_chirps_per_frame;
+  if (h->planned) {
+    info->L_total = P.L_total; info->sample_offset = P.sample_offset; info->nfft = P.nfft;
+    info->ncol_total = P.ncol_total;
+    if (P.valid > 0) { info->col_begin = P.col_begin; info->ncol_local = P.col_end - P.col_begin; }
+    info->n_dtft_bins = (uint32_t)P.nb; info->n_refined = P.n_refined;
+    info->pmax_raw = P.pmax_raw;
+  }
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_process_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const fmcw_frame_out* out) {
+  if (!h) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  FrameDev d{};
+  bool any_host = false;
+  fmcw_status s = run_frames(h, iq, n_frames, out, d, any_host);
+  if (s != FMCW_OK) return s;
+  s = copy_frame_outputs(h, n_frames, out, d);
+  if (s != FMCW_OK) return s;
+  if (any_host) CK(cudaStreamSynchronize(h->stream), "synchronize");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const fmcw_frame_out* fout,
+                     const fmcw_stft_out* sout) {
+  if (!h) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  FrameDev d{};
+  bool any_host = false;
+  fmcw_status s = run_frames(h, iq, n_frames, fout, d, any_host);
+  if (s != FMCW_OK) return s;
+  s = copy_frame_outputs(h, n_frames, fout, d);
+  if (s != FMCW_OK) return s;
+  const uint64_t L_up = n_frames * h->cfg.num_chirps_per_frame;
+  const uint64_t cols_up = L_up >= h->cfg.window_length ? (L_up - h->cfg.overlap) / h->geom.hop : 0;
+  s = run_stft(h, true, 0, 0, 0, 0, true, 0.0, sout, cols_up);
+  if (s != FMCW_OK) return s;
+  if (any_host) {
+    CK(cudaStreamSynchronize(h->stream), "synchronize");
+    if (!h->have_info) { s = read_info(h); if (s != FMCW_OK) return s; }
+    if (h->plan_host.valid == 0) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length slow-time samples");
+  }
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_stft(fmcw_handle* h, const float* x, uint64_t L, const fmcw_stft_out* sout) {
+  if (!h || !x) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (L < h->cfg.window_length) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length samples");
+  CK(h->xc.ensure((L + h->cfg.window_length) * 4), "alloc signal");
+  CK(cudaMemcpyAsync(h->xc.p, x, L * 4, is_device_ptr(x) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream),
+     "copy signal");
+  h->frames_done = false; h->planned = false; h->halo = 0; h->n_frames = 0;
+  const uint64_t cols = (L - h->cfg.overlap) / h->geom.hop;
+  return run_stft(h, false, L, 0, L, L, true, 0.0, sout, cols);
+}
+
+fmcw_status fmcw_get_slow_time(fmcw_handle* h, float* dst, uint64_t first, uint64_t count) {
+  if (!h || (!dst && count)) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  if (!h->have_info) { fmcw_status s = read_info(h); if (s != FMCW_OK) return s; }
+  const uint64_t L = h->n_det_host * h->cfg.num_chirps_per_frame;
+  if (first + count > L) return fail(h, FMCW_ERR_SIZE, "slow-time range out of bounds");
+  if (!count) return FMCW_OK;
+  const bool dev = is_device_ptr(dst);
+  CK(cudaMemcpyAsync(dst, h->xc.as<float>() + first, count * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream),
+     "copy slow-time samples");
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_set_halo(fmcw_handle* h, const float* src, uint64_t count) {
+  if (!h || (!src && count)) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  if (count >= h->cfg.window_length) return fail(h, FMCW_ERR_SIZE, "halo longer than window_length-1");
+  if (!h->have_info) { fmcw_status s = read_info(h); if (s != FMCW_OK) return s; }
+  const uint64_t L = h->n_det_host * h->cfg.num_chirps_per_frame;
+  if (count)
+    CK(cudaMemcpyAsync(h->xc.as<float>() + L, src, count * 4,
+                       is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream), "copy halo");
+  h->halo = count; h->planned = false;
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_stft_local_max(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset, double* pmax_raw_local) {
+  if (!h || !pmax_raw_local) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  if (!h->have_info) { fmcw_status s = read_info(h); if (s != FMCW_OK) return s; }
+  if (L_total < h->cfg.window_length) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length slow-time samples");
+  const uint64_t L = h->n_det_host * h->cfg.num_chirps_per_frame;
+  if (sample_offset + L > L_total) return fail(h, FMCW_ERR_SIZE, "shard exceeds L_total");
+  CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, L_total, sample_offset, L, L + h->halo,
+                      h->n_chunks, h->stream), "stft plan kernel");
+  h->planned = true; h->plan_L = L_total; h->plan_off = sample_offset; h->plan_avail = L + h->halo;
+  CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream), "stft max kernels");
+  fmcw_status s = read_info(h);
+  if (s != FMCW_OK) return s;
+  *pmax_raw_local = h->plan_host.pmax_raw;
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_stft_sharded(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset, double pmax_raw_global,
+                              const fmcw_stft_out* sout) {
+  if (!h) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  if (!h->have_info) { fmcw_status s = read_info(h); if (s != FMCW_OK) return s; }
+  if (!(pmax_raw_global > 0.0)) return fail(h, FMCW_ERR_NO_DATA, "global maximum must be positive");
+  const uint64_t L = h->n_det_host * h->cfg.num_chirps_per_frame;
+  if (h->planned && (h->plan_L != L_total || h->plan_off != sample_offset || h->plan_avail != L + h->halo)) h->planned = false;
+  const uint64_t cols = L / h->geom.hop + 1;
+  return run_stft(h, false, L_total, sample_offset, L, L + h->halo, false, pmax_raw_global, sout, cols);
+}
+
+fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, uint64_t col_begin, uint64_t ncol, double* time,
+                           double* frequency, uint64_t* nfft_out, uint64_t* ncol_total) {
+  if (!cfg) return FMCW_ERR_POINTER;
+  std::string why;
+  fmcw_status vs = validate(cfg, why);
+  if (vs != FMCW_OK) return vs;
+  const uint32_t win = cfg->window_length, hop = win - cfg->overlap;
+  const unsigned long long nfft = 1ull << nextpow2_u64(L_total);
+  const double fs = 1.0 / cfg->PRT;
+  if (nfft_out) *nfft_out = nfft;
+  if (ncol_total) *ncol_total = L_total >= win ? (L_total - cfg->overlap) / hop : 0;
+  if (time)
+    for (uint64_t i = 0; i < ncol; ++i) time[i] = ((double)win / 2.0 + (double)((col_begin + i) * hop)) / fs;   // RP:276
+  if (frequency) {
+    const uint32_t nq = cfg->MAX_FREQ_BINS;
+    const double df = fs / (double)nfft;
+    const double d1 = std::log10(df), d2 = std::log10((double)(nfft / 2) * df);               // RP:294-296
+    for (uint32_t q = 0; q < nq; ++q) {
+      double y = d1 + ((double)q * (d2 - d1)) / (double)(nq - 1);
+      if (q == 0) y = d1;
+      if (q == nq - 1) y = d2;
+      frequency[q] = std::pow(10.0, y);
+    }
+  }
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, uint64_t frame, uint32_t chirp,
+                                float* out) {
+  if (!h || !iq || !out) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  const fmcw_config& c = h->cfg;
+  if (frame >= n_frames || chirp >= c.num_chirps_per_frame) return fail(h, FMCW_ERR_SIZE, "frame / chirp out of range");
+  const size_t frame_words = (size_t)c.num_Rx_antennas * c.num_chirps_per_frame * c.num_ADC_samples_per_chirp;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(iq) + frame * frame_words;
+  if (!is_device_ptr(iq)) {
+    CK(h->iq_stage.ensure(frame_words * 4), "alloc iq staging");
+    CK(cudaMemcpyAsync(h->iq_stage.p, src, frame_words * 4, cudaMemcpyHostToDevice, h->stream), "H2D frame");
+    src = h->iq_stage.as<uint32_t>();
+  }
+  CK(h->o_rmax.ensure(NR * 4), "alloc");
+  ChainParams p{};
+  p.iq = src; p.n_frames = 1; p.NTS = c.num_ADC_samples_per_chirp; p.PN = c.num_chirps_per_frame;
+  p.n_rx = c.num_Rx_antennas; p.rx_sel = c.rx_select; p.ND = c.Doppler_fft_size;
+  p.nts_fft = p.NTS < (uint32_t)NR ? p.NTS : (uint32_t)NR;
+  p.win_tab = h->win_tab.as<float4>(); p.tw_pair = h->tw_pair.as<float2>();
+  p.tw_re = h->tw_re.as<float>(); p.tw_im = h->tw_im.as<float>();
+  p.dop_tw = h->dop_tw.as<float2>(); p.dop_win = h->dop_win.as<float>();
+  p.bin_lo = NR; p.bin_hi = -1;   // no detection work
+  p.range_thr = 0.f; p.dop_thr = 0.f; p.peak_mode = 0;
+  const bool dev = is_device_ptr(out);
+  float* d_spec = dev ? out : h->o_rmax.as<float>();
+  p.spec_out = d_spec; p.spec_frame = 0; p.spec_chirp = chirp;
+  CK(launch_frame_chain(p, h->stream), "frame chain kernel");
+  if (!dev) CK(cudaMemcpyAsync(out, d_spec, NR * 4, cudaMemcpyDeviceToHost, h->stream), "D2H spectrum");
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_synth_frames(fmcw_handle* h, const double* tables, uint32_t n_scat, uint64_t seed, uint64_t frame0,
+                              uint64_t n_frames, double sigma, double dc, double rx_step, int16_t* iq_out) {
+  if (!h || !tables || !iq_out) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  const fmcw_config& c = h->cfg;
+  const double* d_tab = tables;
+  if (!is_device_ptr(tables)) {
+    CK(h->synth_tab.ensure((size_t)n_frames * n_scat * 4 * sizeof(double) + 16), "alloc scene tables");
+    CK(cudaMemcpyAsync(h->synth_tab.p, tables, (size_t)n_frames * n_scat * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream),
+       "H2D scene tables");
+    d_tab = h->synth_tab.as<double>();
+  }
+  const size_t bytes = (size_t)n_frames * c.num_Rx_antennas * c.num_chirps_per_frame * c.num_ADC_samples_per_chirp * 4;
+  const bool dev = is_device_ptr(iq_out);
+  int16_t* d_out = iq_out;
+  if (!dev) { CK(h->iq_stage.ensure(bytes), "alloc iq staging"); d_out = h->iq_stage.as<int16_t>(); }
+  CK(launch_synth(d_tab, n_scat, seed, frame0, n_frames, c.num_Rx_antennas, c.num_chirps_per_frame,
+                  c.num_ADC_samples_per_chirp, sigma, dc, rx_step, d_out, h->stream), "synth kernel");
+  if (!dev) CK(cudaMemcpyAsync(iq_out, d_out, bytes, cudaMemcpyDeviceToHost, h->stream), "D2H iq");
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  return FMCW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Internal declarations shared by the kernels and the C ABI of libfmcw_cuda (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fmcw {
+
+constexpr int NR = 256;           // range_fft_size (RP:118); the radix-16 x radix-16 core is built for it
+constexpr int MAX_ND = 64;        // Doppler_fft_size upper bound
+constexpr int MAX_NQ = 1024;      // MAX_FREQ_BINS upper bound (RP:293)
+constexpr int MAX_CHUNKS = 32;    // query chunks per spectrogram column
+constexpr int CHAIN_THREADS = 256;
+constexpr int CHAIN_WARPS = CHAIN_THREADS / 32;
+constexpr int XCH_STRIDE = 17;    // float2 stride between k1 rows of the in-warp transpose (bank-conflict free)
+constexpr int XCH_CHIRP = 16 * XCH_STRIDE;   // 272 float2 per chirp
+
+// ---- per-frame chain (RP:199-260) -------------------------------------------------------------
+struct ChainParams {
+  const uint32_t* iq;        // int16 (I,Q) pairs, [frame][rx][chirp][sample]
+  uint64_t n_frames;
+  uint32_t NTS, PN, n_rx, rx_sel, ND;
+  uint32_t nts_fft;          // min(NTS, NR): samples that enter the FFT (fft(x,256,1) truncates, RP:205)
+  const float4* win_tab;     // [nts_fft] {gw, h_re, h_im, 0}: xw = gw*(NTS*code - sum) - h
+  const float2* tw_pair;     // [16][16] W_256^(s*k1)
+  const float*  tw_re;       // [272] skewed W_256^k table (index k + k/16)
+  const float*  tw_im;
+  const float2* dop_tw;      // [ND] W_ND^k
+  const float*  dop_win;     // [min(PN,ND)] first taps of 2*chebwin(PN) (RP:139, 219)
+  int32_t bin_lo, bin_hi;    // range gate, 0-based inclusive (RP:126-127 through f_search_peak)
+  float range_thr, dop_thr;
+  int32_t peak_mode;
+  // outputs, device pointers, any may be null
+  float* range_max_abs; int32_t* detected; int32_t* range_bin; float* range_mag;
+  int32_t* doppler_bin; float2* doppler_row; float* slow_mag;
+  // optional: range spectrum of one (frame, chirp) (RP:410-411)
+  float* spec_out; uint64_t spec_frame; uint32_t spec_chirp;
+};
+
+size_t chain_smem_bytes(uint32_t PN);
+cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st);
+
+// ---- compaction of the detected frames' slow-time rows (RP:257-260) ------------------------------
+struct CompactParams {
+  const int32_t* detected; uint64_t n_frames; uint32_t PN;
+  const float* slow_mag;      // [n_frames][PN]
+  float* xc;                  // compacted magnitudes
+  uint32_t* det_list;         // [n_frames] frame index of the k-th detection
+  unsigned long long* n_det;  // device scalar
+};
+cudaError_t launch_compact(const CompactParams& p, cudaStream_t st);
+
+// ---- STFT plan (device resident; RP:273, 293-299 restated) ----------------------------------------
+struct StftPlan {
+  unsigned long long L_total, nfft, ncol_total, col_begin, col_end, sample_offset, L_avail;
+  int log2nfft, nb, nq, n_chunks, valid;
+  unsigned int n_hard, n_refined, pad;
+  float lb_max;                 // max_t max(S0^2, 2|S(w1)|^2) (lower bound of the global max)
+  float pad2;
+  double pmax_raw;              // final global max of c_j |S|^2
+  int chunk_q0[MAX_CHUNKS + 1]; // query range of each chunk (multiples of 32 except the last end)
+  int chunk_p0[MAX_CHUNKS + 1]; // first bin position each chunk needs
+};
+
+struct StftTables {             // device arrays owned by the handle
+  StftPlan* plan;
+  int* bins;                    // [nb_max] fine-grid bin of position p
+  float* kcb;                   // [nb_max] K*log2(c_p), c_p = 1 for DC/Nyquist else 2
+  int* qpos;                    // [nq] position p_q of the lower bracket bin of query q
+  float* aq;                    // [nq] interpolation weight
+  int* qend;                    // [nb_max+1] queries [qend[p-1], qend[p]) complete when position p is known
+  float* coef;                  // [nb_max][2*half] cos((m+d)w), sin((m+d)w)
+  float* win;                   // [win] kaiser window (host computed, float64 -> float32)
+  unsigned int* hard_list;      // columns whose max needs the exhaustive search
+  unsigned int hard_cap;
+  int nb_max;
+};
+
+struct StftGeom { uint32_t win, hop, nq; double fs; };
+
+cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
+                             unsigned long long L_total_host, unsigned long long sample_offset,
+                             unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
+                             cudaStream_t st);
+cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st);
+cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
+cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
+                             unsigned long long capacity_cols, unsigned long long ld_cols, int layout,
+                             int* d_err, cudaStream_t st);
+
+// ---- synthetic scene generator ------------------------------------------------------------------
+cudaError_t launch_synth(const double* tables, uint32_t n_scat, uint64_t seed, uint64_t frame0, uint64_t n_frames,
+                         uint32_t n_rx, uint32_t PN, uint32_t NTS, double sigma, double dc, double rx_step,
+                         int16_t* out, cudaStream_t st);
+
+}  // namespace fmcw

@@ -1,0 +1,343 @@
+// Per-frame chain of the reference (radar_processing.m RP:199-260), one CTA per frame:
+//   unpack int16 I/Q -> calibration + IF scale + fast-time mean removal (RP:203-204, done on exact
+//   integers) -> 2*blackman window -> 256-point range FFT (RP:205) -> max |.| over chirps (RP:210)
+//   -> f_search_peak (RP:211) -> slow-time row at the selected bin (RP:259) -> mean removal over chirps,
+//   2*chebwin window, ND-point Doppler FFT, fftshift (RP:217-219) -> first-max + threshold (RP:233-238).
+//
+// FFT core: 256 = 16 x 16.  Sixteen lanes own one chirp; each lane runs a radix-16 butterfly in
+// registers on the stride-16 samples (pruned for the zero padding), multiplies by W_256^(s*k1),
+// transposes through a private, bank-conflict-free slice of shared memory (only __syncwarp, the two
+// chirps of a warp never leave the warp) and runs the second radix-16.  Nothing of the 256 x PN
+// range cube is written to HBM (RP:207's range_tx1rx1_complete is never materialised): the slow-time
+// row of the one selected bin is re-evaluated as a single-bin DFT from the L1/L2-resident samples.
+#include "fmcw_internal.cuh"
+
+namespace fmcw {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }   // a * (-j)
+__device__ __forceinline__ float2 mul_pj(float2 a) { return make_float2(-a.y, a.x); }   // a * (+j)
+
+// forward 4-point DFT in place: (a0,a1,a2,a3) -> (X0,X1,X2,X3)
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+  a0 = cadd(s02, s13);
+  a2 = csub(s02, s13);
+  a1 = cadd(d02, mul_mj(d13));
+  a3 = cadd(d02, mul_pj(d13));
+}
+// same with a2 = a3 = 0 / with a1 = a2 = a3 = 0 (zero padding of the range FFT)
+__device__ __forceinline__ void dft4_z2(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 x0 = a0, x1 = a1;
+  a0 = cadd(x0, x1);
+  a2 = csub(x0, x1);
+  a1 = cadd(x0, mul_mj(x1));
+  a3 = cadd(x0, mul_pj(x1));
+}
+__device__ __forceinline__ void dft4_z1(float2& a0, float2& a1, float2& a2, float2& a3) { a1 = a0; a2 = a0; a3 = a0; }
+
+// forward 16-point DFT, natural order in and out.  NZ = number of non-zero groups of four inputs
+// (v[4*NZ..15] are treated as zero and never read).
+template <int NZ>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+  // n = 4*n1 + n2: stage A is a DFT over n1 for every n2; result a[n2][k1] kept in v[4*k1 + n2]
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) {
+    if (NZ >= 3) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    else if (NZ == 2) dft4_z2(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    else dft4_z1(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+  }
+  // twiddles W_16^(n2*k1)
+  v[4 * 1 + 1] = cmul(v[4 * 1 + 1], make_float2(C1, -S1));   // m = 1
+  v[4 * 1 + 2] = cmul(v[4 * 1 + 2], make_float2(R2, -R2));   // m = 2
+  v[4 * 1 + 3] = cmul(v[4 * 1 + 3], make_float2(S1, -C1));   // m = 3
+  v[4 * 2 + 1] = cmul(v[4 * 2 + 1], make_float2(R2, -R2));   // m = 2
+  v[4 * 2 + 2] = mul_mj(v[4 * 2 + 2]);                       // m = 4
+  v[4 * 2 + 3] = cmul(v[4 * 2 + 3], make_float2(-R2, -R2));  // m = 6
+  v[4 * 3 + 1] = cmul(v[4 * 3 + 1], make_float2(S1, -C1));   // m = 3
+  v[4 * 3 + 2] = cmul(v[4 * 3 + 2], make_float2(-R2, -R2));  // m = 6
+  v[4 * 3 + 3] = cmul(v[4 * 3 + 3], make_float2(-C1, S1));   // m = 9
+  // stage B: DFT over n2 for every k1 -> X[k1 + 4*k2] in v[4*k1 + k2]
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  // transpose the 4x4 register tile to natural order
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) { float2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+size_t chain_smem_bytes(uint32_t PN) {
+  size_t b = (size_t)CHAIN_WARPS * 2 * XCH_CHIRP * sizeof(float2);   // transpose slices (34,816 B)
+  b += 256 * sizeof(float2);                                          // tw_pair
+  b += 2 * 272 * sizeof(float);                                       // skewed W_256
+  b += NR * sizeof(float4);                                           // window / calibration table
+  b += NR * sizeof(float);                                            // rmax
+  b += (size_t)PN * sizeof(int2);                                     // per-chirp integer sums
+  b += (size_t)PN * sizeof(float2);                                   // slow-time row
+  b += MAX_ND * sizeof(float2) + MAX_ND * sizeof(float);              // Doppler twiddles + window
+  b += 64 * sizeof(unsigned long long);                               // reduction scratch
+  return b;
+}
+
+template <int NZ>
+__global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const ChainParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* xch = reinterpret_cast<float2*>(smem_raw);
+  float2* s_twp = xch + CHAIN_WARPS * 2 * XCH_CHIRP;
+  float* s_twre = reinterpret_cast<float*>(s_twp + 256);
+  float* s_twim = s_twre + 272;
+  float4* s_win = reinterpret_cast<float4*>(s_twim + 272);
+  float* s_rmax = reinterpret_cast<float*>(s_win + NR);
+  int2* s_csum = reinterpret_cast<int2*>(s_rmax + NR);
+  float2* s_row = reinterpret_cast<float2*>(s_csum + p.PN);
+  float2* s_dtw = s_row + p.PN;
+  float* s_dwin = reinterpret_cast<float*>(s_dtw + MAX_ND);
+  unsigned long long* s_red = reinterpret_cast<unsigned long long*>(s_dwin + MAX_ND);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = lane & 15, half = lane >> 4;
+  const uint32_t NTS = p.NTS, PN = p.PN, ND = p.ND;
+  const int ndc = (int)min(PN, ND);
+
+  // ---- tables (once per CTA; the grid is persistent over frames) ----
+  s_twp[tid] = p.tw_pair[tid];
+  for (int i = tid; i < 272; i += CHAIN_THREADS) { s_twre[i] = p.tw_re[i]; s_twim[i] = p.tw_im[i]; }
+  s_win[tid] = (tid < (int)p.nts_fft) ? p.win_tab[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < (int)ND) s_dtw[tid] = p.dop_tw[tid];
+  if (tid < ndc) s_dwin[tid] = p.dop_win[tid];
+  __syncthreads();
+
+  float2* my_x = xch + (warp * 2 + half) * XCH_CHIRP;
+
+  for (uint64_t f = blockIdx.x; f < p.n_frames; f += gridDim.x) {
+    const uint32_t* fbase = p.iq + ((f * p.n_rx + p.rx_sel) * (uint64_t)PN) * NTS;
+    float mx[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx[i] = 0.f;
+
+    // ================= pass 1: range FFT of every chirp, running max of |X|^2 =================
+    for (uint32_t pair = warp; pair * 2 < PN; pair += CHAIN_WARPS) {
+      const uint32_t c = pair * 2 + half;
+      const bool active = c < PN;
+      const uint32_t* cb = fbase + (uint64_t)(active ? c : 0) * NTS;
+      int ci[4 * NZ], cq[4 * NZ];
+      int sumI = 0, sumQ = 0;
+#pragma unroll
+      for (int r = 0; r < 4 * NZ; ++r) {
+        const uint32_t n = s + 16 * r;
+        uint32_t w = 0;
+        if (active && n < NTS) w = __ldg(cb + n);
+        ci[r] = (int)(short)(w & 0xffffu);
+        cq[r] = (int)w >> 16;
+        sumI += ci[r];
+        sumQ += cq[r];
+      }
+      if (active)
+        for (uint32_t n = s + NR; n < NTS; n += 16) {   // samples past the FFT length still enter the mean (RP:204)
+          uint32_t w = __ldg(cb + n);
+          sumI += (int)(short)(w & 0xffffu);
+          sumQ += (int)w >> 16;
+        }
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) {
+        sumI += __shfl_xor_sync(0xffffffffu, sumI, m);
+        sumQ += __shfl_xor_sync(0xffffffffu, sumQ, m);
+      }
+      if (active && s == 0) s_csum[c] = make_int2(sumI, sumQ);
+
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 4 * NZ; ++r) {
+        const float4 wt = s_win[s + 16 * r];
+        // (code - mean)*NTS is an exact integer; one rounding in the fused multiply-add
+        const float dI = (float)((int)NTS * ci[r] - sumI), dQ = (float)((int)NTS * cq[r] - sumQ);
+        const bool live = (uint32_t)(s + 16 * r) < p.nts_fft;
+        v[r] = live ? make_float2(fmaf(wt.x, dI, -wt.y), fmaf(wt.x, dQ, -wt.z)) : make_float2(0.f, 0.f);
+      }
+      dft16<NZ>(v);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        float2 a = (k1 == 0) ? v[0] : cmul(v[k1], s_twp[k1 * 16 + s]);
+        my_x[k1 * XCH_STRIDE + s] = a;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) v[n2] = my_x[s * XCH_STRIDE + n2];
+      __syncwarp();
+      dft16<4>(v);   // v[k2] = X[s + 16*k2]
+      if (p.spec_out != nullptr && active && f == p.spec_frame && c == p.spec_chirp) {
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) p.spec_out[s + 16 * k2] = sqrtf(fmaf(v[k2].x, v[k2].x, v[k2].y * v[k2].y));
+      }
+      if (active) {
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) mx[k2] = fmaxf(mx[k2], fmaf(v[k2].x, v[k2].x, v[k2].y * v[k2].y));
+      }
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) mx[k2] = fmaxf(mx[k2], __shfl_xor_sync(0xffffffffu, mx[k2], 16));
+    __syncthreads();   // every warp is done with its transpose slice; reuse it for the cross-warp max
+    float* s_mx = reinterpret_cast<float*>(xch);
+    if (half == 0) {
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) s_mx[warp * NR + s + 16 * k2] = mx[k2];
+    }
+    __syncthreads();
+    {
+      float m = s_mx[tid];
+#pragma unroll
+      for (int w = 1; w < CHAIN_WARPS; ++w) m = fmaxf(m, s_mx[w * NR + tid]);
+      const float r = sqrtf(m);
+      s_rmax[tid] = r;
+      if (p.range_max_abs) p.range_max_abs[f * NR + tid] = r;
+    }
+    __syncthreads();
+
+    // ================= f_search_peak (RP:211; shim definition, see oracle) =================
+    unsigned long long key = 0ull;
+    if (tid >= 2 && tid <= NR - 3 && tid >= p.bin_lo && tid <= p.bin_hi) {
+      const float fp = s_rmax[tid];
+      if (fp >= p.range_thr && fp >= s_rmax[tid - 2] && fp >= s_rmax[tid - 1] && fp > s_rmax[tid + 1] &&
+          fp > s_rmax[tid + 2]) {
+        const unsigned long long lo = 0xffffffffull - (unsigned)tid;
+        key = (p.peak_mode == 0) ? (((unsigned long long)__float_as_uint(fp) << 32) | lo) : ((1ull << 32) | lo);
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { unsigned long long o = shfl_xor_u64(key, m); key = o > key ? o : key; }
+    if (lane == 0) s_red[warp] = key;
+    __syncthreads();
+    key = s_red[0];
+#pragma unroll
+    for (int w = 1; w < CHAIN_WARPS; ++w) key = s_red[w] > key ? s_red[w] : key;
+    const bool det = key != 0ull;
+    const int kbin = det ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : -1;
+    __syncthreads();   // s_red is reused below
+
+    if (tid == 0) {
+      if (p.detected) p.detected[f] = det ? 1 : 0;
+      if (p.range_bin) p.range_bin[f] = kbin;
+      if (p.range_mag) p.range_mag[f] = det ? s_rmax[kbin] : 0.f;
+    }
+    if (!det) {
+      if (p.slow_mag) for (uint32_t c = tid; c < PN; c += CHAIN_THREADS) p.slow_mag[f * PN + c] = 0.f;
+      if (p.doppler_row && tid < (int)ND) p.doppler_row[f * ND + tid] = make_float2(0.f, 0.f);
+      if (p.doppler_bin && tid == 0) p.doppler_bin[f] = (int)ND / 2;
+      continue;
+    }
+
+    // ================= pass 2: slow-time row at the selected bin (single-bin DFT) =================
+    for (uint32_t c = warp; c < PN; c += CHAIN_WARPS) {
+      const uint32_t* cb = fbase + (uint64_t)c * NTS;
+      const int2 cs = s_csum[c];
+      float ar = 0.f, ai = 0.f;
+      for (uint32_t n = lane; n < p.nts_fft; n += 32) {
+        const uint32_t w = __ldg(cb + n);
+        const float4 wt = s_win[n];
+        const float dI = (float)((int)NTS * (int)(short)(w & 0xffffu) - cs.x);
+        const float dQ = (float)((int)NTS * ((int)w >> 16) - cs.y);
+        const float xr = fmaf(wt.x, dI, -wt.y), xi = fmaf(wt.x, dQ, -wt.z);
+        const uint32_t k = (n * (uint32_t)kbin) & (NR - 1);
+        const float tr = s_twre[k + (k >> 4)], ti = s_twim[k + (k >> 4)];
+        ar = fmaf(xr, tr, fmaf(-xi, ti, ar));
+        ai = fmaf(xr, ti, fmaf(xi, tr, ai));
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        ar += __shfl_xor_sync(0xffffffffu, ar, m);
+        ai += __shfl_xor_sync(0xffffffffu, ai, m);
+      }
+      if (lane == 0) s_row[c] = make_float2(ar, ai);
+    }
+    __syncthreads();
+
+    // slow-time magnitudes (RP:259 + RP:270) and the mean over all PN chirps (RP:217)
+    float sr = 0.f, si = 0.f;
+    for (uint32_t c = tid; c < PN; c += CHAIN_THREADS) {
+      const float2 r = s_row[c];
+      if (p.slow_mag) p.slow_mag[f * PN + c] = sqrtf(fmaf(r.x, r.x, r.y * r.y));
+      sr += r.x;
+      si += r.y;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, m);
+      si += __shfl_xor_sync(0xffffffffu, si, m);
+    }
+    float2* s_sum = reinterpret_cast<float2*>(s_red);
+    if (lane == 0) s_sum[warp] = make_float2(sr, si);
+    __syncthreads();
+    float mr = 0.f, mi = 0.f;
+#pragma unroll
+    for (int w = 0; w < CHAIN_WARPS; ++w) { mr += s_sum[w].x; mi += s_sum[w].y; }
+    mr /= (float)PN;
+    mi /= (float)PN;
+    __syncthreads();
+
+    // Doppler FFT over the first min(PN, ND) chirps, fftshift, first max, threshold (RP:219, 233-238)
+    if (warp == 0) {
+      unsigned long long dk = 0ull;
+      for (int i0 = 0; i0 < (int)ND; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < (int)ND) {
+          const int k = (i + (int)ND / 2) & ((int)ND - 1);
+          float dr = 0.f, di = 0.f;
+          for (int c = 0; c < ndc; ++c) {
+            const float2 r = s_row[c];
+            const float w = s_dwin[c];
+            const float xr = (r.x - mr) * w, xi = (r.y - mi) * w;
+            const float2 t = s_dtw[(c * k) & ((int)ND - 1)];
+            dr = fmaf(xr, t.x, fmaf(-xi, t.y, dr));
+            di = fmaf(xr, t.y, fmaf(xi, t.x, di));
+          }
+          if (p.doppler_row) p.doppler_row[f * ND + i] = make_float2(dr, di);
+          const float a = sqrtf(fmaf(dr, dr, di * di));
+          const unsigned long long kk = ((unsigned long long)__float_as_uint(a) << 32) | (0xffffffffull - (unsigned)i);
+          dk = kk > dk ? kk : dk;
+        }
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) { unsigned long long o = shfl_xor_u64(dk, m); dk = o > dk ? o : dk; }
+      if (lane == 0 && p.doppler_bin) {
+        const float val = __uint_as_float((unsigned)(dk >> 32));
+        const int idx = (int)(0xffffffffu - (unsigned)(dk & 0xffffffffull));
+        p.doppler_bin[f] = (val >= p.dop_thr) ? idx : (int)ND / 2;
+      }
+    }
+    __syncthreads();   // s_row / s_csum are rewritten by the next frame
+  }
+}
+
+cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st) {
+  if (p.n_frames == 0) return cudaSuccess;
+  const size_t smem = chain_smem_bytes(p.PN);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t max_grid = (uint64_t)sms * 3 * 8;   // persistent over frames; tables are loaded once per CTA
+  const unsigned grid = (unsigned)(p.n_frames < max_grid ? p.n_frames : max_grid);
+  cudaError_t e;
+#define FMCW_LAUNCH_CHAIN(NZ)                                                                              \
+  do {                                                                                                     \
+    e = cudaFuncSetAttribute(frame_chain_kernel<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                        \
+    frame_chain_kernel<NZ><<<grid, CHAIN_THREADS, smem, st>>>(p);                                          \
+  } while (0)
+  if (p.nts_fft <= 64) FMCW_LAUNCH_CHAIN(1);
+  else if (p.nts_fft <= 128) FMCW_LAUNCH_CHAIN(2);
+  else FMCW_LAUNCH_CHAIN(4);
+#undef FMCW_LAUNCH_CHAIN
+  return cudaGetLastError();
+}
+
+}  // namespace fmcw

@@ -1,0 +1,593 @@
+// Cross-frame STFT micro-Doppler spectrogram (radar_processing.m RP:270-299), restated so that it
+// never materialises the (nfft/2+1) x ncol PSD matrix of the literal code:
+//   * nfft = 2^nextpow2(L) (RP:273) only fixes the fine frequency grid F_j = j*fs/nfft;
+//   * interp1 onto the 1024 log-spaced frequencies (RP:293-299) touches only the fine-grid bins that
+//     bracket a query; the windowed DTFT is evaluated at exactly those bins (~1.1k-1.7k);
+//   * the global normalisation max(P) (RP:282-283) is found exactly from per-column bounds.
+// Everything that depends on L (nfft, bins, coefficients, chunks) is planned ON THE DEVICE, so the
+// fused path frames -> compaction -> STFT runs without a host round trip.
+#include "fmcw_internal.cuh"
+
+namespace fmcw {
+
+constexpr float K_DB = 6.020599913279624f;   // 20*log10(2): psd = 20*log10(P/max) (RP:283)
+constexpr int NP_MAX = 320;                  // bin positions a chunk may hold in shared memory
+constexpr int MAIN_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom g, const unsigned long long* d_ndet,
+                                                         uint32_t PN, unsigned long long L_total_host,
+                                                         unsigned long long sample_offset,
+                                                         unsigned long long L_local_host, unsigned long long L_avail_host,
+                                                         int n_chunks_req) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_wsum[32];
+  __shared__ unsigned long long s_nfft;
+  __shared__ int s_valid;
+  StftPlan* P = t.plan;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = (int)g.nq;
+  const int win = (int)g.win, hop = (int)g.hop, nov = win - hop;
+
+  if (tid == 0) {
+    unsigned long long L = L_total_host, Lloc = L_local_host, Lav = L_avail_host;
+    if (d_ndet) { L = *d_ndet * PN; Lloc = L; Lav = L; }
+    P->L_total = L; P->sample_offset = sample_offset; P->L_avail = Lav;
+    P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0;
+    int ok = (L >= (unsigned long long)win) ? 1 : 0;
+    int lg = (L <= 1) ? 0 : 64 - __clzll((long long)(L - 1));
+    unsigned long long nfft = 1ull << lg;
+    P->log2nfft = lg; P->nfft = nfft;
+    unsigned long long ncol = ok ? (L - nov) / hop : 0;
+    P->ncol_total = ncol;
+    unsigned long long cb = (sample_offset + hop - 1) / hop;
+    unsigned long long ce = (sample_offset + Lloc + hop - 1) / hop;
+    if (ce > ncol) ce = ncol;
+    // every owned column needs win samples inside [offset, offset + L_avail)
+    if (sample_offset + Lav >= (unsigned long long)win) {
+      unsigned long long last = (sample_offset + Lav - win) / hop + 1;
+      if (ce > last) ce = last;
+    } else ce = cb;
+    if (cb > ce) cb = ce;
+    P->col_begin = cb; P->col_end = ce;
+    P->nq = nq;
+    s_nfft = nfft; s_valid = ok;
+    P->valid = ok;
+  }
+  __syncthreads();
+  if (!s_valid) { if (tid == 0) { P->nb = 0; P->n_chunks = 0; } return; }
+  const unsigned long long nfft = s_nfft;
+  const double df = g.fs / (double)nfft;
+  const long long jmax = (long long)(nfft / 2) - 1;
+
+  // query frequency q -> bracket bin j, weight a (matlab logspace + interp1 'linear','extrap')
+  long long j = 0; double a = 0.0;
+  if (tid < nq) {
+    const double d1 = log10(df), d2 = log10((double)(nfft / 2) * df);
+    double y = d1 + ((double)tid * (d2 - d1)) / (double)(nq - 1);
+    if (tid == 0) y = d1;
+    if (tid == nq - 1) y = d2;
+    const double fq = pow(10.0, y);
+    j = (long long)floor(fq / df);
+    if (j < 0) j = 0;
+    if (j > jmax) j = jmax;
+    a = (fq - (double)j * df) / df;
+  }
+  // new bins contributed by query q: 2 / 1 / 0
+  long long jprev = __shfl_up_sync(0xffffffffu, j, 1);
+  __shared__ long long s_lastj[32];
+  if (lane == 31) s_lastj[warp] = j;
+  __syncthreads();
+  if (lane == 0 && warp > 0) jprev = s_lastj[warp - 1];
+  int c = 0;
+  if (tid < nq) c = (tid == 0) ? 2 : (j == jprev ? 0 : (j == jprev + 1 ? 1 : 2));
+  // inclusive block scan
+  int x = c;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) { int o = __shfl_up_sync(0xffffffffu, x, m); if (lane >= m) x += o; }
+  if (lane == 31) s_wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_wsum[lane], y2 = v;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) { int o = __shfl_up_sync(0xffffffffu, y2, m); if (lane >= m) y2 += o; }
+    s_wsum[lane] = y2 - v;
+  }
+  __syncthreads();
+  const int cum = x + s_wsum[warp];
+  const int pq = cum - 2;
+  s_scan[tid] = (tid < nq) ? pq : 0x7fffffff;
+  __shared__ int s_nb;
+  if (tid == nq - 1) s_nb = cum;
+  __syncthreads();
+  const int nb = s_nb;
+  if (nb > t.nb_max) { if (tid == 0) { P->valid = -2; P->nb = nb; } return; }
+  if (tid < nq) {
+    t.bins[pq] = (int)j;
+    t.bins[pq + 1] = (int)j + 1;
+    t.qpos[tid] = pq;
+    t.aq[tid] = (float)a;
+    // qend[p] = first query whose lower position is >= p
+    if (tid == 0) { for (int p = 0; p <= pq; ++p) t.qend[p] = 0; }
+    else { const int pp = s_scan[tid - 1]; for (int p = pp + 1; p <= pq; ++p) t.qend[p] = tid; }
+    if (tid == nq - 1) for (int p = pq + 1; p <= nb; ++p) t.qend[p] = nq;
+  }
+  __syncthreads();
+  __threadfence_block();
+  // per-position constants and DTFT coefficients (float64 sincospi of an exactly reduced argument)
+  const int half = win / 2;
+  const int odd = win & 1;
+  const long long mod = (long long)(2 * nfft);
+  for (int i = tid; i < nb * half; i += blockDim.x) {
+    const int p = i / half, m = i - p * half;
+    const long long bin = t.bins[p];
+    const long long twod = odd ? (2 * m + 2) : (2 * m + 1);       // 2*delta, delta = tap distance from the centre
+    const long long r = (twod * bin) % mod;
+    double sn, cs;
+    sincospi((double)r / (double)nfft, &sn, &cs);
+    t.coef[(size_t)p * 2 * half + m] = (float)cs;
+    t.coef[(size_t)p * 2 * half + half + m] = (float)sn;
+  }
+  for (int p = tid; p < nb; p += blockDim.x) {
+    const long long bin = t.bins[p];
+    t.kcb[p] = (bin == 0 || bin == (long long)(nfft / 2)) ? 0.f : K_DB;
+  }
+  // chunks of queries (multiples of 32) holding about nb / n_chunks positions each
+  if (tid == 0) {
+    int nch = n_chunks_req < 1 ? 1 : (n_chunks_req > MAX_CHUNKS ? MAX_CHUNKS : n_chunks_req);
+    int cnt = 0;
+    P->chunk_q0[0] = 0; P->chunk_p0[0] = s_scan[0];
+    int last_q = 0;
+    for (int k = 1; k < nch; ++k) {
+      const int target = (int)(((long long)k * nb) / nch);
+      int q = last_q + 32;
+      while (q < nq && s_scan[q] < target) q += 32;
+      if (q >= nq) break;
+      ++cnt;
+      P->chunk_q0[cnt] = q; P->chunk_p0[cnt] = s_scan[q];
+      last_q = q;
+    }
+    ++cnt;
+    P->chunk_q0[cnt] = nq; P->chunk_p0[cnt] = nb;
+    P->n_chunks = cnt;
+    P->nb = nb;
+    int bad = 0;
+    for (int k = 0; k < cnt; ++k) {
+      const int p1 = s_scan[P->chunk_q0[k + 1] - 1] + 1;
+      if (p1 - P->chunk_p0[k] + 1 > NP_MAX) bad = 1;
+    }
+    if (bad) P->valid = -3;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// global maximum of c_j |S_t(w_j)|^2 over the whole fine grid
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float atomic_max_nonneg(float* addr, float v) {
+  return __uint_as_float(atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v)));
+}
+
+// per column: S0 = sum y, S1 = |S(w_1)|^2; lower bound max(S0^2, c_1 |S1|^2)
+__global__ void __launch_bounds__(256) stft_colstat_kernel(StftTables t, StftGeom g, const float* __restrict__ x) {
+  const StftPlan* P = t.plan;
+  if (P->valid <= 0) return;
+  __shared__ float s_w[1024];
+  __shared__ float s_c1[1024];
+  __shared__ float s_red[8];
+  const int win = (int)g.win, half = win / 2, odd = win & 1;
+  const int p1 = (t.bins[0] == 1) ? 0 : 1;
+  const float c1 = (t.kcb[p1] > 0.f) ? 2.f : 1.f;
+  for (int i = threadIdx.x; i < win; i += blockDim.x) s_w[i] = t.win[i];
+  for (int i = threadIdx.x; i < 2 * half; i += blockDim.x) s_c1[i] = t.coef[(size_t)p1 * 2 * half + i];
+  __syncthreads();
+  const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
+  float best = 0.f;
+  for (unsigned long long col = cb + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; col < ce;
+       col += (unsigned long long)gridDim.x * blockDim.x) {
+    const float* xs = x + (col * g.hop - off);
+    float s0 = 0.f, re = 0.f, im = 0.f;
+    const int cidx = half;   // centre tap for odd windows
+    for (int m = 0; m < half; ++m) {
+      const int lo = odd ? (cidx - 1 - m) : (half - 1 - m), hi = odd ? (cidx + 1 + m) : (half + m);
+      const float ylo = s_w[lo] * xs[lo], yhi = s_w[hi] * xs[hi];
+      s0 += ylo + yhi;
+      re = fmaf(ylo + yhi, s_c1[m], re);
+      im = fmaf(ylo - yhi, s_c1[half + m], im);
+    }
+    if (odd) { const float yc = s_w[cidx] * xs[cidx]; s0 += yc; re += yc; }
+    const float lb = fmaxf(s0 * s0, c1 * fmaf(re, re, im * im));
+    best = fmaxf(best, lb);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, m));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) best = fmaxf(best, s_red[w]);
+    if (best > 0.f) atomic_max_nonneg(&t.plan->lb_max, best);
+  }
+}
+
+// Columns whose trivial bound 2*(sum|y|)^2 exceeds the lower bound get a certificate: for y >= 0 the
+// spectrum is non-increasing on [0, pi/(win-1)], and on [pi/(win-1), pi] a uniform grid plus the
+// Lipschitz constant sum|n-c||y_n| bounds it.  Columns that fail go to the exhaustive list.
+__global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom g, const float* __restrict__ x) {
+  StftPlan* P = t.plan;
+  if (P->valid <= 0) return;
+  __shared__ float s_w[1024];
+  const int win = (int)g.win;
+  for (int i = threadIdx.x; i < win; i += blockDim.x) s_w[i] = t.win[i];
+  __syncthreads();
+  const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
+  const float lb = P->lb_max;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long first = cb + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  // warp-uniform trip count
+  for (unsigned long long col0 = first - lane; col0 < ce; col0 += stride) {
+    const unsigned long long col = col0 + lane;
+    bool cand = false, nonneg = true;
+    float sabs = 0.f, dl = 0.f;
+    if (col < ce) {
+      const float* xs = x + (col * g.hop - off);
+      const float c0 = 0.5f * (float)(win - 1);
+      for (int n = 0; n < win; ++n) {
+        const float y = s_w[n] * xs[n];
+        nonneg = nonneg && (y >= 0.f);
+        sabs += fabsf(y);
+        dl = fmaf(fabsf((float)n - c0), fabsf(y), dl);
+      }
+      cand = 2.f * sabs * sabs > lb;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, cand);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const unsigned long long ccol = col0 + src;
+      const bool c_nonneg = __shfl_sync(0xffffffffu, (int)nonneg, src) != 0;
+      const float c_dl = __shfl_sync(0xffffffffu, dl, src);
+      bool fail = !c_nonneg;
+      if (!fail && win > 2) {
+        const float* xs = x + (ccol * g.hop - off);
+        const float w_lo = 3.14159265358979f / (float)(win - 1);
+        const int G = 32 * win;
+        const float delta = (3.14159265358979f - w_lo) / (float)G;
+        const float slack = c_dl * delta * 0.5f;
+        float worst = 0.f;
+        for (int gi = lane; gi < G; gi += 32) {
+          const float w = w_lo + ((float)gi + 0.5f) * delta;
+          float sn, cs;
+          sincosf(w, &sn, &cs);
+          // Horner in z = exp(-jw)
+          float ar = 0.f, ai = 0.f;
+          for (int n = win - 1; n >= 0; --n) {
+            const float tr = fmaf(ar, cs, ai * sn), ti = fmaf(ai, cs, -ar * sn);
+            ar = tr + s_w[n] * xs[n];
+            ai = ti;
+          }
+          const float mag = sqrtf(fmaf(ar, ar, ai * ai)) + slack;
+          worst = fmaxf(worst, mag);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, m));
+        fail = 2.f * worst * worst * 1.00002f > lb;
+      }
+      if (lane == 0) {
+        atomicAdd(&P->n_refined, 1u);
+        if (fail) {
+          const unsigned slot = atomicAdd(&P->n_hard, 1u);
+          if (slot < t.hard_cap) t.hard_list[slot] = (unsigned)(ccol - cb);
+          else P->valid = -5;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void atomic_max_double_nonneg(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// Exhaustive scan of the fine grid for the (rare) columns that have no certificate; float64.
+__global__ void __launch_bounds__(256) stft_hard_kernel(StftTables t, StftGeom g, const float* __restrict__ x) {
+  StftPlan* P = t.plan;
+  if (P->valid <= 0) return;
+  const unsigned nh = P->n_hard < t.hard_cap ? P->n_hard : t.hard_cap;
+  if (nh == 0) return;
+  __shared__ double s_y[1024];
+  __shared__ double s_red[8];
+  const int win = (int)g.win;
+  const unsigned long long nfft = P->nfft, nyq = nfft / 2;
+  double best = 0.0;
+  for (unsigned h = 0; h < nh; ++h) {
+    const unsigned long long col = P->col_begin + t.hard_list[h];
+    const float* xs = x + (col * g.hop - P->sample_offset);
+    __syncthreads();
+    for (int i = threadIdx.x; i < win; i += blockDim.x) s_y[i] = (double)t.win[i] * (double)xs[i];
+    __syncthreads();
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j <= nyq;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+      double sn, cs;
+      sincospi(2.0 * (double)j / (double)nfft, &sn, &cs);
+      double ar = 0.0, ai = 0.0;
+      for (int n = win - 1; n >= 0; --n) {
+        const double tr = ar * cs + ai * sn, ti = ai * cs - ar * sn;
+        ar = tr + s_y[n];
+        ai = ti;
+      }
+      const double p2 = (ar * ar + ai * ai) * ((j == 0 || j == nyq) ? 1.0 : 2.0);
+      best = p2 > best ? p2 : best;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, best, m); best = o > best ? o : best; }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) best = s_red[w] > best ? s_red[w] : best;
+    if (best > 0.0) atomic_max_double_nonneg(&P->pmax_raw, best);
+  }
+}
+
+__global__ void stft_finalize_max_kernel(StftTables t) {
+  StftPlan* P = t.plan;
+  if (P->valid <= 0) return;
+  const double lb = (double)P->lb_max;
+  if (lb > P->pmax_raw) P->pmax_raw = lb;
+}
+
+__global__ void stft_set_max_kernel(StftTables t, double v) { t.plan->pmax_raw = v; }
+
+// ------------------------------------------------------------------------------------------------
+// main kernel: one thread = CPT spectrogram columns, all of one chunk's bins
+// ------------------------------------------------------------------------------------------------
+template <int QF>
+__device__ __forceinline__ void flush_stage(float* stage, int ncols, unsigned long long tile_col0,
+                                            unsigned long long col_end, unsigned long long col_begin, float* out,
+                                            int nq, int qbase, int nvalid, int lane) {
+  __syncwarp();
+  if (lane < QF) {
+    for (int c = 0; c < ncols; ++c) {
+      const unsigned long long col = tile_col0 + c;
+      if (col < col_end && lane < nvalid) out[(col - col_begin) * (unsigned long long)nq + qbase + lane] = stage[c * (QF + 1) + lane];
+    }
+  }
+  __syncwarp();
+}
+
+template <int HALF, int CPT, int QF, int LAYOUT>
+__global__ void __launch_bounds__(MAIN_THREADS, (CPT <= 2 ? 3 : 2))
+stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out,
+                 unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err) {
+  const StftPlan* P = t.plan;
+  if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
+  constexpr int WIN = 2 * HALF;
+  constexpr int COLS_W = 32 * CPT;                 // columns per warp
+  constexpr int COLS_B = MAIN_THREADS * CPT;       // columns per CTA task
+  extern __shared__ __align__(16) float s_main[];
+  float* s_coef = s_main;                                  // [NP_MAX][WIN]
+  float* s_kcb = s_coef + NP_MAX * WIN;                    // [NP_MAX]
+  int* s_qend = reinterpret_cast<int*>(s_kcb + NP_MAX);    // [NP_MAX]
+  float* s_aq = reinterpret_cast<float*>(s_qend + NP_MAX); // [MAX_NQ]
+  float* s_ws = s_aq + MAX_NQ;                             // [WIN]
+  float* s_stage = s_ws + WIN;                             // [warps][COLS_W][QF+1] (time-major layout only)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
+  const unsigned long long ncl = ce - cb;
+  if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
+  const int nq = P->nq, n_chunks = P->n_chunks;
+  if (tid < WIN) s_ws[tid] = (float)((double)t.win[tid] / sqrt(P->pmax_raw));
+  const unsigned long long n_cblk = (ncl + COLS_B - 1) / COLS_B;
+  const unsigned long long n_tasks = n_cblk * (unsigned long long)n_chunks;
+  float* stage = s_stage + ((LAYOUT == 0) ? warp * COLS_W * (QF + 1) : 0);
+
+  for (unsigned long long task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+    const int ch = (int)(task % (unsigned long long)n_chunks);
+    const unsigned long long cblk = task / (unsigned long long)n_chunks;
+    const int q0 = P->chunk_q0[ch], q1 = P->chunk_q0[ch + 1];
+    const int p0 = P->chunk_p0[ch];
+    const int p1 = t.qpos[q1 - 1] + 1;
+    const int np = p1 - p0 + 1;
+    __syncthreads();   // previous task is done with the tables
+    for (int i = tid; i < np * WIN / 4; i += MAIN_THREADS)
+      reinterpret_cast<float4*>(s_coef)[i] = reinterpret_cast<const float4*>(t.coef + (size_t)p0 * WIN)[i];
+    for (int i = tid; i < np; i += MAIN_THREADS) { s_kcb[i] = t.kcb[p0 + i]; s_qend[i] = t.qend[p0 + i]; }
+    for (int i = tid; i < q1 - q0; i += MAIN_THREADS) s_aq[i] = t.aq[q0 + i];
+    __syncthreads();
+
+    // window * x, folded into even / odd parts: |S|^2 = (sum e_m cos)^2 + (sum o_m sin)^2
+    float e[CPT][HALF], o[CPT][HALF];
+    const unsigned long long warp_col0 = cb + cblk * COLS_B + (unsigned long long)warp * COLS_W;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      unsigned long long col = warp_col0 + c * 32 + lane;
+      if (col >= ce) col = ce - 1;
+      const float* xs = x + (col * g.hop - off);
+#pragma unroll
+      for (int m = 0; m < HALF; ++m) {
+        const float ylo = s_ws[HALF - 1 - m] * __ldg(xs + HALF - 1 - m), yhi = s_ws[HALF + m] * __ldg(xs + HALF + m);
+        e[c][m] = ylo + yhi;
+        o[c][m] = ylo - yhi;
+      }
+    }
+    float prev[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) prev[c] = 0.f;
+    int qi = 0;   // queries of this chunk emitted so far
+
+    for (int ip = 0; ip < np; ++ip) {
+      const float4* cf = reinterpret_cast<const float4*>(s_coef + ip * WIN);
+      float re[CPT], im[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) { re[c] = 0.f; im[c] = 0.f; }
+      float cs[WIN];
+#pragma unroll
+      for (int v = 0; v < WIN / 4; ++v) {
+        const float4 f = cf[v];
+        cs[4 * v] = f.x; cs[4 * v + 1] = f.y; cs[4 * v + 2] = f.z; cs[4 * v + 3] = f.w;
+      }
+#pragma unroll
+      for (int m = 0; m < HALF; ++m) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          re[c] = fmaf(e[c][m], cs[m], re[c]);
+          im[c] = fmaf(o[c][m], cs[HALF + m], im[c]);
+        }
+      }
+      float db[CPT];
+      const float kc = s_kcb[ip];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) db[c] = fmaf(K_DB, __log2f(fmaf(re[c], re[c], im[c] * im[c])), kc);
+      if (ip > 0) {
+        int qa = s_qend[ip - 1] - q0, qb = s_qend[ip] - q0;
+        qa = qa < 0 ? 0 : qa;
+        qb = qb > (q1 - q0) ? (q1 - q0) : qb;
+        for (int q = qa; q < qb; ++q) {
+          const float a = s_aq[q];
+          if (LAYOUT == 0) {
+            const int slot = q & (QF - 1);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) stage[(c * 32 + lane) * (QF + 1) + slot] = fmaf(a, db[c] - prev[c], prev[c]);
+            if (slot == QF - 1)
+              flush_stage<QF>(stage, COLS_W, warp_col0, ce, cb, out, nq, q0 + (q & ~(QF - 1)), QF, lane);
+          } else {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              const unsigned long long col = warp_col0 + c * 32 + lane;
+              if (col < ce) out[(unsigned long long)(q0 + q) * ld_cols + (col - cb)] = fmaf(a, db[c] - prev[c], prev[c]);
+            }
+          }
+        }
+        qi = qb;
+      }
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) prev[c] = db[c];
+    }
+    if (LAYOUT == 0) {
+      const int rem = (q1 - q0) & (QF - 1);
+      if (rem) flush_stage<QF>(stage, COLS_W, warp_col0, ce, cb, out, nq, q0 + ((q1 - q0) & ~(QF - 1)), rem, lane);
+    }
+    (void)qi;
+  }
+}
+
+// Generic window length (any win >= 2, any hop): one thread per column, taps staged in shared memory.
+// Correct for every configuration; the specialised kernel above is the fast path for the reference's
+// window_length = 20.
+template <int LAYOUT>
+__global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeom g, const float* __restrict__ x,
+                                                           float* __restrict__ out, unsigned long long capacity_cols,
+                                                           unsigned long long ld_cols, int* d_err) {
+  const StftPlan* P = t.plan;
+  if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
+  extern __shared__ float s_dyn[];   // [2*half + odd][128] even / odd parts (+ centre), thread-minor
+  const int win = (int)g.win, half = win / 2, odd = win & 1;
+  const int tid = threadIdx.x;
+  const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
+  const unsigned long long ncl = ce - cb;
+  if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
+  const int nq = P->nq, nb = P->nb;
+  const float inv = (float)(1.0 / sqrt(P->pmax_raw));
+  const unsigned long long n_blk = (ncl + 127) / 128;
+  for (unsigned long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+    unsigned long long col = cb + blk * 128 + tid;
+    const bool act = col < ce;
+    if (!act) col = ce - 1;
+    const float* xs = x + (col * g.hop - off);
+    for (int m = 0; m < half; ++m) {
+      const int lo = odd ? (half - 1 - m) : (half - 1 - m), hi = odd ? (half + 1 + m) : (half + m);
+      const float ylo = t.win[lo] * inv * xs[lo], yhi = t.win[hi] * inv * xs[hi];
+      s_dyn[m * 128 + tid] = ylo + yhi;
+      s_dyn[(half + m) * 128 + tid] = ylo - yhi;
+    }
+    const float yc = odd ? t.win[half] * inv * xs[half] : 0.f;
+    float prev = 0.f;
+    for (int p = 0; p < nb; ++p) {
+      const float* cf = t.coef + (size_t)p * 2 * half;
+      float re = yc, im = 0.f;
+      for (int m = 0; m < half; ++m) {
+        re = fmaf(s_dyn[m * 128 + tid], __ldg(cf + m), re);
+        im = fmaf(s_dyn[(half + m) * 128 + tid], __ldg(cf + half + m), im);
+      }
+      const float db = fmaf(K_DB, __log2f(fmaf(re, re, im * im)), t.kcb[p]);
+      if (p > 0 && act) {
+        for (int q = t.qend[p - 1]; q < t.qend[p]; ++q) {
+          const float v = fmaf(t.aq[q], db - prev, prev);
+          if (LAYOUT == 0) out[(col - cb) * (unsigned long long)nq + q] = v;
+          else out[(unsigned long long)q * ld_cols + (col - cb)] = v;
+        }
+      }
+      prev = db;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+
+cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
+                             unsigned long long L_total_host, unsigned long long sample_offset,
+                             unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
+                             cudaStream_t st) {
+  stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st) {
+  const int grid = sm_count() * 8;
+  stft_colstat_kernel<<<grid, 256, 0, st>>>(t, g, x);
+  stft_refine_kernel<<<grid, 256, 0, st>>>(t, g, x);
+  stft_hard_kernel<<<sm_count() * 4, 256, 0, st>>>(t, g, x);
+  stft_finalize_max_kernel<<<1, 1, 0, st>>>(t);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st) {
+  stft_set_max_kernel<<<1, 1, 0, st>>>(t, pmax_raw);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
+                             unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
+                             cudaStream_t st) {
+  const int sms = sm_count();
+  if (g.win == 20) {
+    constexpr int HALF = 10, CPT = 2, QF = 16;
+    const size_t base = (size_t)(NP_MAX * 2 * HALF + NP_MAX + NP_MAX + MAX_NQ + 2 * HALF) * sizeof(float);
+    cudaError_t e;
+    if (layout == 0) {
+      const size_t smem = base + (size_t)(MAIN_THREADS / 32) * 32 * CPT * (QF + 1) * sizeof(float);
+      e = cudaFuncSetAttribute(stft_main_kernel<HALF, CPT, QF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      stft_main_kernel<HALF, CPT, QF, 0><<<sms * 3, MAIN_THREADS, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+    } else {
+      e = cudaFuncSetAttribute(stft_main_kernel<HALF, CPT, QF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+      if (e != cudaSuccess) return e;
+      stft_main_kernel<HALF, CPT, QF, 1><<<sms * 3, MAIN_THREADS, base, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+    }
+  } else {
+    const size_t smem = (size_t)(2 * (g.win / 2)) * 128 * sizeof(float);
+    cudaError_t e;
+    if (layout == 0) {
+      e = cudaFuncSetAttribute(stft_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      stft_generic_kernel<0><<<sms * 4, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+    } else {
+      e = cudaFuncSetAttribute(stft_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      stft_generic_kernel<1><<<sms * 4, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+    }
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fmcw

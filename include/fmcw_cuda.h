@@ -1,0 +1,182 @@
+/* libfmcw_cuda -- C ABI of the B200-native range-Doppler-STFT chain.
+ *
+ * Drop-in boundary for the per-frame loop and the STFT block of the reference
+ * (alepnabil/fmcw_radar_processing, radar-etl-pipeline/radar_processing.m, "RP"):
+ *   RP:197-261  per-frame chain ('no' branch)      -> fmcw_process_frames / fmcw_run
+ *   RP:265      max over chirps for all frames     -> fmcw_frame_out.range_max_abs
+ *   RP:270-299  STFT + dB + log-frequency resample -> fmcw_stft / fmcw_run
+ *   RP:457-566  same per 100-frame batch ('yes')   -> fmcw_run on a frame sub-range
+ *   RP:410-411  range spectrum of one (frame,chirp)-> fmcw_range_spectrum
+ *   RP:89-179   configuration                      -> fmcw_config (fmcw_configurations, RP:645-672)
+ * The reference has no FFI of its own (pure MATLAB); the MEX gateway (mex/) and the
+ * Node-API addon (node/) bind exactly these entry points, see INTEGRATION.md.
+ *
+ * Conventions: plain C, no exceptions, every call returns an fmcw_status.  All buffers
+ * are caller-owned; each may be a host or a device pointer (detected with
+ * cudaPointerGetAttributes).  Indices are 0-based (MATLAB index - 1).  A handle is
+ * not re-entrant (a second concurrent call returns FMCW_ERR_BUSY); distinct handles
+ * are independent and may be used from any thread.  There is no CPU fallback.
+ */
+#ifndef FMCW_CUDA_H
+#define FMCW_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FMCW_API __declspec(dllexport)
+#else
+#define FMCW_API __attribute__((visibility("default")))
+#endif
+
+typedef enum fmcw_status {
+  FMCW_OK = 0,
+  FMCW_ERR_CONFIG = 1,   /* inconsistent or unsupported fmcw_config field */
+  FMCW_ERR_POINTER = 2,  /* NULL or mismatched pointer argument */
+  FMCW_ERR_CUDA = 3,     /* a CUDA runtime call or kernel failed */
+  FMCW_ERR_NCCL = 4,     /* reserved for the collective layer */
+  FMCW_ERR_OOM = 5,      /* device or host allocation failed */
+  FMCW_ERR_BUSY = 6,     /* another call is in flight on this handle */
+  FMCW_ERR_SIZE = 7,     /* a size argument is out of range (e.g. capacity too small) */
+  FMCW_ERR_NO_DATA = 8,  /* fewer than window_length slow-time samples (RP:269, RP:534) */
+  FMCW_ERR_STATE = 9     /* call order violated (e.g. STFT before frames were processed) */
+} fmcw_status;
+
+enum { FMCW_PEAK_STRONGEST = 0, FMCW_PEAK_FIRST = 1 };
+enum { FMCW_LAYOUT_TIME_MAJOR = 0,  /* intensity[col][n_freq]: MATLAB's 1024 x ncol column-major */
+       FMCW_LAYOUT_FREQ_MAJOR = 1   /* intensity[n_freq][ld_cols]: jsonencode / NumPy row order  */ };
+
+/* Field names follow the reference's fmcw_configurations struct (RP:645-672); the values
+ * are what RP:89-179 computes.  struct_size must be sizeof(fmcw_config) of the caller. */
+typedef struct fmcw_config {
+  uint32_t struct_size;
+  uint32_t num_Tx_antennas;             /* RP:102 (unused by the chain) */
+  uint32_t num_Rx_antennas;             /* RP:103 */
+  uint32_t num_ADC_samples_per_chirp;   /* NTS, RP:109 */
+  uint32_t num_chirps_per_frame;        /* PN,  RP:112 */
+  uint32_t range_fft_size;              /* RP:118, must be 256 */
+  uint32_t Doppler_fft_size;            /* RP:119, power of two <= 64 */
+  uint32_t max_num_targets;             /* RP:129, must be 1 */
+  uint32_t window_length;               /* RP:178 */
+  uint32_t overlap;                     /* RP:179 */
+  uint32_t MAX_FREQ_BINS;               /* RP:293, <= 1024 */
+  uint32_t rx_select;                   /* 0-based RX processed; the reference uses RX 1 -> 0 (RP:202) */
+  uint32_t peak_mode;                   /* FMCW_PEAK_* (f_search_peak is not shipped upstream) */
+  uint32_t reserved0;
+  double frame_time;                    /* RP:91 */
+  double PRT;                           /* RP:97 */
+  double Bandwidth;                     /* RP:100 */
+  double carrier_frequency;             /* RP:106 */
+  double sampling_frequency;            /* RP:115 (unused by the chain) */
+  double IF_scale;                      /* RP:121 */
+  double range_threshold;               /* RP:123 */
+  double Doppler_threshold;             /* RP:124 */
+  double min_distance;                  /* RP:126 */
+  double max_distance;                  /* RP:127 */
+  double lambda;                        /* RP:133 */
+  double Hz_to_mps_constant;            /* RP:135 */
+  double R_max;                         /* RP:142 */
+  double dist_per_bin;                  /* RP:147 */
+  double fD_max;                        /* RP:152 */
+  double fD_per_bin;                    /* RP:153 */
+  double kaiser_beta;                   /* RP:276 literal 3 */
+  double adc_scale;                     /* parser normalisation, 4095 (f_parse_data2 shim) */
+} fmcw_config;
+
+typedef struct fmcw_handle fmcw_handle;
+
+/* Per-frame outputs (RP:197-261).  Any pointer may be NULL to skip that output. */
+typedef struct fmcw_frame_out {
+  float*   range_max_abs;  /* [n_frames][range_fft_size]  abs(max(range_fft,[],2)), RP:210/265 */
+  int32_t* detected;       /* [n_frames] 1 if f_search_peak returned a target (RP:213) */
+  int32_t* range_bin;      /* [n_frames] tgt_range_idx(1)-1, or -1 */
+  float*   range_mag;      /* [n_frames] tgt_range_mag(1), or 0 (RP:245) */
+  int32_t* doppler_bin;    /* [n_frames] tgt_doppler_idx(1)-1 in the fftshifted row (RP:233-238) */
+  float*   doppler_row;    /* [n_frames][Doppler_fft_size][2] fftshifted complex row, RP:219 */
+  float*   slow_time_mag;  /* [n_frames][PN] abs of the stored range-FFT row at the selected bin, RP:259/270 */
+} fmcw_frame_out;
+
+/* STFT outputs (RP:270-299). */
+typedef struct fmcw_stft_out {
+  float*   intensity;      /* interp_intensity, layout per `layout` */
+  uint64_t capacity_cols;  /* columns the intensity buffer can hold */
+  uint64_t ld_cols;        /* row stride for FMCW_LAYOUT_FREQ_MAJOR (0 = capacity_cols) */
+  uint32_t layout;         /* FMCW_LAYOUT_* */
+  uint32_t reserved0;
+} fmcw_stft_out;
+
+/* Scalars describing a finished run (host memory, filled by fmcw_get_info). */
+typedef struct fmcw_run_info {
+  uint64_t n_frames;       /* frames processed by the last fmcw_process_frames / fmcw_run */
+  uint64_t n_detected;     /* frames with a target */
+  uint64_t L_local;        /* slow-time samples held by this handle (n_detected * PN) */
+  uint64_t L_total;        /* length of the whole (possibly sharded) slow-time signal */
+  uint64_t sample_offset;  /* global index of this handle's first sample */
+  uint64_t nfft;           /* 2^nextpow2(L_total), RP:273 */
+  uint64_t ncol_total;     /* spectrogram columns of the whole signal */
+  uint64_t col_begin;      /* first global column written by this handle */
+  uint64_t ncol_local;     /* columns written by this handle */
+  uint32_t n_dtft_bins;    /* distinct fine-grid bins evaluated per column */
+  uint32_t n_refined;      /* columns that needed the exhaustive max search */
+  double   pmax_raw;       /* max over the one-sided fine grid of c_j*|S|^2 (un-normalised) */
+} fmcw_run_info;
+
+FMCW_API const char* fmcw_version(void);
+FMCW_API const char* fmcw_status_string(fmcw_status s);
+
+/* calib_data: the parser's calibration row vector [I_rx1 Q_rx1 I_rx2 Q_rx2 ...] in normalised
+ * units, length 2*num_Rx_antennas*N_cal with N_cal a multiple of NTS (RP:167-174).  Host pointer. */
+FMCW_API fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64_t calib_len,
+                                 int device, fmcw_handle** out);
+FMCW_API void        fmcw_destroy(fmcw_handle* h);
+FMCW_API const char* fmcw_last_error(const fmcw_handle* h);
+FMCW_API void*       fmcw_get_stream(fmcw_handle* h);      /* cudaStream_t all work is queued on */
+FMCW_API fmcw_status fmcw_synchronize(fmcw_handle* h);
+FMCW_API fmcw_status fmcw_get_info(fmcw_handle* h, fmcw_run_info* info);   /* synchronises */
+
+/* iq: int16 [n_frames][num_Rx_antennas][PN][NTS][2] ADC codes (I,Q interleaved), host or device. */
+FMCW_API fmcw_status fmcw_process_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,
+                                         const fmcw_frame_out* out);
+
+/* Fused single-GPU path: frames -> compaction -> STFT of the detected slow-time signal.
+ * Asynchronous when every buffer is device memory; call fmcw_get_info for the sizes. */
+FMCW_API fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,
+                              const fmcw_frame_out* fout, const fmcw_stft_out* sout);
+
+/* STFT of an arbitrary non-negative sequence x[L] (host or device): RP:270-299 on its own. */
+FMCW_API fmcw_status fmcw_stft(fmcw_handle* h, const float* x, uint64_t L, const fmcw_stft_out* sout);
+
+/* Sharded path (one handle per GPU; the collectives between the steps belong to the caller):
+ *   fmcw_process_frames -> fmcw_get_info (n_detected) -> all-gather counts ->
+ *   fmcw_get_slow_time / fmcw_set_halo (neighbour exchange of window_length-1 samples) ->
+ *   fmcw_stft_local_max -> all-reduce(max) -> fmcw_stft_sharded. */
+FMCW_API fmcw_status fmcw_get_slow_time(fmcw_handle* h, float* dst, uint64_t first, uint64_t count);
+FMCW_API fmcw_status fmcw_set_halo(fmcw_handle* h, const float* src, uint64_t count);
+FMCW_API fmcw_status fmcw_stft_local_max(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset,
+                                         double* pmax_raw_local);
+FMCW_API fmcw_status fmcw_stft_sharded(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset,
+                                       double pmax_raw_global, const fmcw_stft_out* sout);
+
+/* Host-side axes in float64: T (RP:276) for columns [col_begin, col_begin+ncol) and
+ * log_freq_bins (RP:293-296).  Either pointer may be NULL. */
+FMCW_API fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, uint64_t col_begin, uint64_t ncol,
+                                    double* time, double* frequency, uint64_t* nfft, uint64_t* ncol_total);
+
+/* Range spectrum abs(range_fft(:, chirp)) of one frame (RP:410-411). out: [range_fft_size] floats. */
+FMCW_API fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,
+                                         uint64_t frame, uint32_t chirp, float* out);
+
+/* Synthetic scene generator: same bits as fmcw_radar_processing_b200/synth.py.
+ * tables: float64 [n_frames][n_scat][4] (A, cycles/sample, cycles/chirp, phase cycles), host or device.
+ * iq_out: device or host int16 [n_frames][n_rx][PN][NTS][2]. */
+FMCW_API fmcw_status fmcw_synth_frames(fmcw_handle* h, const double* tables, uint32_t n_scat, uint64_t seed,
+                                       uint64_t frame0, uint64_t n_frames, double sigma, double dc,
+                                       double rx_step, int16_t* iq_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMCW_CUDA_H */

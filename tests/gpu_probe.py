@@ -1,0 +1,43 @@
+"""Development probe (not a test): prints parity metrics of the CUDA path against the oracle."""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+from tests import helpers as H
+from oracle import fmcw_oracle as O
+from fmcw_radar_processing_b200.api import FmcwCuda
+from fmcw_radar_processing_b200 import synth
+
+for (NTS, PN, nf) in [(128, 64, 60), (64, 16, 80), (256, 256, 6)]:
+    case = H.make_case(n_frames=nf, NTS=NTS, PN=PN)
+    ref = H.oracle_no(case)
+    h = FmcwCuda(case["cfg"], case["calib"])
+    out, inten = h.run(case["iq"])
+    info = h.info()
+    print("shape", NTS, PN, nf, info)
+    print(" det equal", np.array_equal(out["detected"].astype(bool), ref["detected"]),
+          "range_bin equal", np.array_equal(out["range_bin"][ref["detected"]], ref["range_idx"][ref["detected"]] - 1),
+          "doppler_bin equal", np.array_equal(out["doppler_bin"][ref["detected"]], ref["doppler_idx"][ref["detected"]] - 1))
+    print(" range_max_abs err", H.db_errors(out["range_max_abs"], ref["range_tx1rx1_max_abs"].T))
+    d = ref["detected"]
+    print(" range_mag rel", np.abs(out["range_mag"][d] / ref["range_mag"][d] - 1).max())
+    gd = out["doppler_row"][..., 0] + 1j * out["doppler_row"][..., 1]
+    print(" doppler_row err", H.db_errors(np.abs(gd[d]), np.abs(ref["doppler_rows"][d])))
+    slow_ref = np.abs(ref["slow_time_signal_all_frames"]).reshape(-1, PN)
+    print(" slow mag rel", np.abs(out["slow_time_mag"][d] / slow_ref - 1).max())
+    st = ref["stft"]
+    nc = info["ncol_local"]
+    print(" ncol", nc, st["intensity"].shape, "nfft", info["nfft"], st["nfft"], "pmax rel", info["pmax_raw"] / st["pmax_raw"] - 1)
+    print(" spectrogram e2e err", H.spectrogram_errors(inten[:nc].T, st["intensity"]))
+    # STFT in isolation on the float32-rounded oracle signal
+    x32 = np.abs(ref["slow_time_signal_all_frames"]).astype(np.float32)
+    ref2 = O.stft_restated(x32.astype(np.float64), case["ocfg"])
+    g2 = h.stft(x32)
+    print(" spectrogram isolated err", H.spectrogram_errors(g2[:nc].T, ref2["intensity"]), "min dB", ref2["intensity"].min())
+    g3 = h.stft(x32, layout=1)
+    print(" layouts agree", np.array_equal(g3[:, :nc], g2[:nc].T))
+    T, F, nfft, nct = h.stft_axes(info["L_total"])
+    print(" axes", np.abs(T - st["T"]).max(), np.abs(F / st["frequency"] - 1).max())
+    # generator parity
+    g = h.synth_frames(case["tables"], case["scene"].seed, 0)
+    print(" synth mismatches", int((g != case["iq"]).sum()))
+    h.close()
