@@ -76,6 +76,12 @@ class FmcwCuda:
         self._check(self.lib.fmcw_get_info(self._h, C.byref(inf)))
         return {n: getattr(inf, n) for n, _ in _lib.fmcw_run_info._fields_}
 
+    def timings(self) -> dict:
+        """Device ms of the stages of the last run (CUDA events on the handle's stream)."""
+        ms = (C.c_float * 4)()
+        self._check(self.lib.fmcw_get_timings(self._h, C.byref(ms)))
+        return dict(chain_ms=ms[0], compact_ms=ms[1], plan_max_ms=ms[2], stft_main_ms=ms[3])
+
     # ---- buffers ----
     def alloc_frame_out(self, n_frames: int, device=None) -> dict:
         """Per-frame output buffers: NumPy (host) by default, torch CUDA tensors if ``device`` is given."""

@@ -143,6 +143,8 @@ struct fmcw_handle {
   uint64_t plan_L = 0, plan_off = 0, plan_avail = 0;
   StftPlan plan_host{};
   int n_chunks = 8;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, chain, compact, plan+max, main
+  bool ev_valid[5] = {false, false, false, false, false};
 };
 
 namespace {
@@ -281,9 +283,13 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   p.range_max_abs = d.rmax; p.detected = d.det; p.range_bin = d.rbin; p.range_mag = d.rmag;
   p.doppler_bin = d.dbin; p.doppler_row = d.drow; p.slow_mag = d.slow;
   p.spec_out = nullptr;
+  for (bool& v : h->ev_valid) v = false;
+  CK(cudaEventRecord(h->ev[0], h->stream), "event"); h->ev_valid[0] = true;
   CK(launch_frame_chain(p, h->stream), "frame chain kernel");
+  CK(cudaEventRecord(h->ev[1], h->stream), "event"); h->ev_valid[1] = true;
   CompactParams cp{d.det, n_frames, PN, d.slow, h->xc.as<float>(), h->det_list.as<uint32_t>(), h->ndet.as<unsigned long long>()};
   CK(launch_compact(cp, h->stream), "compaction kernels");
+  CK(cudaEventRecord(h->ev[2], h->stream), "event"); h->ev_valid[2] = true;
   h->n_frames = n_frames; h->frames_done = true; h->have_info = false; h->planned = false; h->halo = 0;
   return FMCW_OK;
 }
@@ -332,8 +338,10 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
     if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream), "stft max kernels");
   }
   if (!compute_max) CK(launch_stft_set_max(h->st, pmax_override, h->stream), "stft set max");
+  CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
   CK(launch_stft_main(h->st, h->geom, h->xc.as<float>(), d_out, cap, d_ld, (int)sout->layout, h->derr.as<int>(), h->stream),
      "stft main kernel");
+  CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
   if (!dev_out) {
     fmcw_status s = read_info(h);
@@ -395,6 +403,8 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   auto bail = [&](fmcw_status s) { fmcw_destroy(h); return s; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(FMCW_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FMCW_ERR_CUDA);
+  for (cudaEvent_t& e : h->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return bail(FMCW_ERR_CUDA);
 
   // ---- calibration (RP:167-174), window (RP:138) and scale (RP:121, 203) folded into one table ----
   std::vector<std::complex<double>> cal(NTS, {0.0, 0.0});
@@ -484,6 +494,7 @@ void fmcw_destroy(fmcw_handle* h) {
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->xc, &h->det_list, &h->ndet, &h->inten,
                    &h->synth_tab};
   for (DevBuf* b : all) b->release();
+  for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -516,6 +527,19 @@ fmcw_status fmcw_get_info(fmcw_handle* h, fmcw_run_info* info) {
     if (P.valid > 0) { info->col_begin = P.col_begin; info->ncol_local = P.col_end - P.col_begin; }
     info->n_dtft_bins = (uint32_t)P.nb; info->n_refined = P.n_refined;
     info->pmax_raw = P.pmax_raw;
+  }
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_get_timings(fmcw_handle* h, float* ms) {
+  if (!h || !ms) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  for (int i = 0; i < 4; ++i) {
+    ms[i] = 0.f;
+    if (h->ev_valid[i] && h->ev_valid[i + 1]) CK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]), "event elapsed");
   }
   return FMCW_OK;
 }

@@ -1,0 +1,138 @@
+"""Frame-sharded multi-GPU run: one process per GPU, contiguous frame ranges,
+``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tests) for the plumbing.
+
+The per-frame chain (RP:197-261) needs no communication.  The STFT (RP:270-299) couples the shards
+through the concatenated slow-time signal only, so exactly three small collectives remain:
+
+1. one all-gather of ``[local length, first window_length-1 samples]`` per rank: gives every
+   shard its global sample offset, the global length L (hence nfft, RP:273) and the halo it needs from the
+   shard(s) to its right -- also when a neighbour detected fewer than window_length-1 samples;
+2. one all-reduce(max) of the scalar normalisation max(P) (RP:282-283);
+3. one all-gather of the per-frame track (range bin, Doppler bin, strength) for the range/speed payload.
+
+Column ownership: a spectrogram column belongs to the shard that owns its first sample, so columns are
+neither duplicated nor lost.  Everything in this file except ``ShardedRun`` is backend agnostic and is
+covered by world_size-2 gloo tests on CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ShardLayout:
+    lengths: list          # local slow-time lengths of every rank
+    offsets: list          # global index of every rank's first sample
+    L_total: int
+    halo: torch.Tensor     # the samples following this rank's last sample (<= window_length-1)
+
+
+def exchange_heads(x_local: torch.Tensor, L_local: int, window_length: int, group=None) -> ShardLayout:
+    """Collective 1.  ``x_local`` holds at least ``min(L_local, window_length-1)`` leading samples of this
+    rank's slow-time magnitude signal (float32, on the backend's device)."""
+    ws, rank = dist.get_world_size(group), dist.get_rank(group)
+    hw = window_length - 1
+    dev = x_local.device
+    msg = torch.zeros(2 + hw, dtype=torch.float32, device=dev)
+    # the length travels as two exact float32 halves (lengths can exceed 2^24)
+    msg[0] = float(L_local & 0xFFFFF)
+    msg[1] = float(L_local >> 20)
+    n_head = min(L_local, hw)
+    if n_head:
+        msg[2:2 + n_head] = x_local[:n_head]
+    gathered = [torch.empty_like(msg) for _ in range(ws)]
+    dist.all_gather(gathered, msg, group=group)
+    heads = torch.stack(gathered)
+    meta = heads[:, :2].to("cpu", torch.float64).numpy()
+    lengths = [int(lo) + (int(hi) << 20) for lo, hi in meta]
+    offsets = [int(v) for v in np.concatenate([[0], np.cumsum(lengths)[:-1]])]
+    # assemble the halo from the heads of the following ranks (skipping short / empty shards)
+    parts, need = [], hw
+    for r in range(rank + 1, ws):
+        if need == 0:
+            break
+        take = min(need, lengths[r], hw)
+        if take:
+            parts.append(heads[r, 2:2 + take])
+            need -= take
+    halo = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.float32, device=dev)
+    return ShardLayout(lengths, offsets, int(sum(lengths)), halo)
+
+
+def allreduce_max(value: float, device, group=None) -> float:
+    """Collective 2."""
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def gather_track(range_bin: torch.Tensor, doppler_bin: torch.Tensor, range_mag: torch.Tensor, frame_counts, group=None):
+    """Collective 3: per-frame track of the whole recording on every rank (12 B per frame)."""
+    ws = dist.get_world_size(group)
+    nmax = max(frame_counts)
+    dev = range_bin.device
+    msg = torch.zeros(3, nmax, dtype=torch.float32, device=dev)
+    n = range_bin.shape[0]
+    msg[0, :n] = range_bin.to(torch.float32)
+    msg[1, :n] = doppler_bin.to(torch.float32)
+    msg[2, :n] = range_mag
+    out = [torch.empty_like(msg) for _ in range(ws)]
+    dist.all_gather(out, msg, group=group)
+    rb = torch.cat([out[r][0, :frame_counts[r]] for r in range(ws)]).to(torch.int32)
+    db = torch.cat([out[r][1, :frame_counts[r]] for r in range(ws)]).to(torch.int32)
+    mg = torch.cat([out[r][2, :frame_counts[r]] for r in range(ws)])
+    return rb, db, mg
+
+
+def owned_columns(offset: int, L_local: int, L_total: int, window_length: int, overlap: int):
+    """[begin, end) of the global spectrogram columns whose first sample lies in this shard."""
+    hop = window_length - overlap
+    ncol = (L_total - overlap) // hop if L_total >= window_length else 0
+    b = -(-offset // hop)
+    e = min(ncol, -(-(offset + L_local) // hop))
+    return min(b, e), e, ncol
+
+
+class ShardedRun:
+    """One rank's share of a frame-sharded recording on its GPU."""
+
+    def __init__(self, handle, group=None, frame_counts=None):
+        self.h = handle
+        self.group = group
+        self.frame_counts = frame_counts      # frames per rank (static); gathered once if not given
+
+    def step(self, iq, out, intensity, layout=0, gather=True):
+        h = self.h
+        dev = iq.device
+        h.process_frames(iq, out)
+        info = h.info()
+        L_local = info["L_local"]
+        win = h.cfg["window_length"]
+        head = torch.zeros(win - 1, dtype=torch.float32, device=dev)
+        n_head = min(L_local, win - 1)
+        if n_head:
+            h.get_slow_time(head, 0, n_head)
+        lay = exchange_heads(head, L_local, win, self.group)
+        rank = dist.get_rank(self.group)
+        halo = lay.halo.contiguous()
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()     # the library works on its own stream
+        h.set_halo(halo, int(halo.numel()))
+        if lay.L_total < win:
+            return dict(layout=lay, ncol_local=0, col_begin=0, pmax_raw=0.0, track=None)
+        local_max = h.stft_local_max(lay.L_total, lay.offsets[rank])
+        pmax = allreduce_max(local_max, dev, self.group)
+        h.stft_sharded(lay.L_total, lay.offsets[rank], pmax, intensity, layout)
+        track = None
+        if gather:
+            if self.frame_counts is None:
+                counts = [None] * dist.get_world_size(self.group)
+                dist.all_gather_object(counts, int(iq.shape[0]), group=self.group)
+                self.frame_counts = counts
+            track = gather_track(out["range_bin"], out["doppler_bin"], out["range_mag"], self.frame_counts, self.group)
+        b, e, ncol = owned_columns(lay.offsets[rank], L_local, lay.L_total, win, h.cfg["overlap"])
+        return dict(layout=lay, ncol_local=e - b, col_begin=b, ncol_total=ncol, pmax_raw=pmax, track=track)

@@ -137,6 +137,11 @@ FMCW_API void*       fmcw_get_stream(fmcw_handle* h);      /* cudaStream_t all w
 FMCW_API fmcw_status fmcw_synchronize(fmcw_handle* h);
 FMCW_API fmcw_status fmcw_get_info(fmcw_handle* h, fmcw_run_info* info);   /* synchronises */
 
+/* Device time in ms of the stages of the last fmcw_run / fmcw_process_frames (CUDA events on the
+ * handle's stream; synchronises): ms[0] frame chain, ms[1] compaction, ms[2] STFT plan + global max,
+ * ms[3] STFT main kernel.  Stages that did not run report 0. */
+FMCW_API fmcw_status fmcw_get_timings(fmcw_handle* h, float* ms);
+
 /* iq: int16 [n_frames][num_Rx_antennas][PN][NTS][2] ADC codes (I,Q interleaved), host or device. */
 FMCW_API fmcw_status fmcw_process_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,
                                          const fmcw_frame_out* out);
