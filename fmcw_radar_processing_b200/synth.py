@@ -52,6 +52,8 @@ class Scene:
     dc: float = 2048.0
     rx_step: float = 0.11   # per-RX phase offset [cycles]
     frame_time: float = 0.15
+    r_min: float = 2.0      # targets walk back and forth between r_min and r_max (inside the 0.9-25 m gate, RP:126-127)
+    r_max: float = 22.0
 
 
 def scene_c1(seed=1):
@@ -75,8 +77,11 @@ def scene_tables(scene: Scene, dist_per_bin: float, range_fft_size: int, PRT: fl
     tab = np.zeros((n_frames, max(1, len(scene.scatterers)), 4), dtype=np.float64)
     for i, s in enumerate(scene.scatterers):
         arg = 2 * np.pi * s.limb_f * t + s.limb_phi
-        R = s.R0 + s.v * t + s.limb_a * np.sin(arg)
-        vr = s.v + s.limb_a * 2 * np.pi * s.limb_f * np.cos(arg)
+        span = scene.r_max - scene.r_min
+        u = np.mod(s.R0 + s.v * t - scene.r_min, 2 * span)          # triangle path: reflect at r_min / r_max
+        fwd = u <= span
+        R = scene.r_min + np.where(fwd, u, 2 * span - u) + s.limb_a * np.sin(arg)
+        vr = np.where(fwd, s.v, -s.v) + s.limb_a * 2 * np.pi * s.limb_f * np.cos(arg)
         tab[:, i, 0] = s.A
         tab[:, i, 1] = (R / dist_per_bin) / range_fft_size
         tab[:, i, 2] = 2.0 * vr * PRT / lam
