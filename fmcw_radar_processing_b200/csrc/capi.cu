@@ -142,7 +142,7 @@ struct fmcw_handle {
   uint64_t n_det_host = 0, halo = 0;
   uint64_t plan_L = 0, plan_off = 0, plan_avail = 0;
   StftPlan plan_host{};
-  int n_chunks = 8;
+  int n_chunks = 12;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, chain, compact, plan+max, main
   bool ev_valid[5] = {false, false, false, false, false};
 };

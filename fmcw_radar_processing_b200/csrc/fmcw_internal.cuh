@@ -53,7 +53,7 @@ cudaError_t launch_compact(const CompactParams& p, cudaStream_t st);
 struct StftPlan {
   unsigned long long L_total, nfft, ncol_total, col_begin, col_end, sample_offset, L_avail;
   int log2nfft, nb, nq, n_chunks, valid;
-  unsigned int n_hard, n_refined, pad;
+  unsigned int n_hard, n_refined, task_counter;
   float lb_max;                 // max_t max(S0^2, 2|S(w1)|^2) (lower bound of the global max)
   float pad2;
   double pmax_raw;              // final global max of c_j |S|^2

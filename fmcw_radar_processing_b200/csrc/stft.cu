@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
     unsigned long long L = L_total_host, Lloc = L_local_host, Lav = L_avail_host;
     if (d_ndet) { L = *d_ndet * PN; Lloc = L; Lav = L; }
     P->L_total = L; P->sample_offset = sample_offset; P->L_avail = Lav;
-    P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0;
+    P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0; P->task_counter = 0;
     int ok = (L >= (unsigned long long)win) ? 1 : 0;
     int lg = (L <= 1) ? 0 : 64 - __clzll((long long)(L - 1));
     unsigned long long nfft = 1ull << lg;
@@ -134,16 +134,18 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
     const long long bin = t.bins[p];
     t.kcb[p] = (bin == 0 || bin == (long long)(nfft / 2)) ? 0.f : K_DB;
   }
-  // chunks of queries (multiples of 32) holding about nb / n_chunks positions each
+  // chunks of queries (multiples of 32) of about equal cost: ~60 issue slots per bin, ~14 per query
   if (tid == 0) {
+    constexpr long long CB = 60, CQ = 14;
     int nch = n_chunks_req < 1 ? 1 : (n_chunks_req > MAX_CHUNKS ? MAX_CHUNKS : n_chunks_req);
+    const long long total = (long long)nb * CB + (long long)nq * CQ;
     int cnt = 0;
     P->chunk_q0[0] = 0; P->chunk_p0[0] = s_scan[0];
     int last_q = 0;
     for (int k = 1; k < nch; ++k) {
-      const int target = (int)(((long long)k * nb) / nch);
+      const long long target = (k * total) / nch;
       int q = last_q + 32;
-      while (q < nq && s_scan[q] < target) q += 32;
+      while (q < nq && (long long)s_scan[q] * CB + (long long)q * CQ < target) q += 32;
       if (q >= nq) break;
       ++cnt;
       P->chunk_q0[cnt] = q; P->chunk_p0[cnt] = s_scan[q];
@@ -336,22 +338,55 @@ __global__ void stft_finalize_max_kernel(StftTables t) {
   if (P->valid <= 0) return;
   const double lb = (double)P->lb_max;
   if (lb > P->pmax_raw) P->pmax_raw = lb;
+  P->task_counter = 0;
 }
 
-__global__ void stft_set_max_kernel(StftTables t, double v) { t.plan->pmax_raw = v; }
+__global__ void stft_set_max_kernel(StftTables t, double v) { t.plan->pmax_raw = v; t.plan->task_counter = 0; }
 
 // ------------------------------------------------------------------------------------------------
 // main kernel: one thread = CPT spectrogram columns, all of one chunk's bins
 // ------------------------------------------------------------------------------------------------
-template <int QF>
-__device__ __forceinline__ void flush_stage(float* stage, int ncols, unsigned long long tile_col0,
-                                            unsigned long long col_end, unsigned long long col_begin, float* out,
-                                            int nq, int qbase, int nvalid, int lane) {
+// shared-memory access through 32-bit shared-window addresses (keeps the address arithmetic out of the
+// uniform datapath, which otherwise re-derives the generic base every iteration)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Writes the staged [COLS_W][QF] tile of one warp as full rows of QF consecutive log-frequency bins per
+// column (time-major layout: 4*QF contiguous bytes per column).
+template <int QF, int COLS_W>
+__device__ __forceinline__ void flush_stage(uint32_t a_stage, int ncols_valid, float* __restrict__ out_warp,
+                                            unsigned long long row_stride, int qbase, int nvalid, int lane) {
+  constexpr int CPI = 32 / QF;          // columns written per iteration
   __syncwarp();
-  if (lane < QF) {
-    for (int c = 0; c < ncols; ++c) {
-      const unsigned long long col = tile_col0 + c;
-      if (col < col_end && lane < nvalid) out[(col - col_begin) * (unsigned long long)nq + qbase + lane] = stage[c * (QF + 1) + lane];
+  const int sub = lane / QF, ql = lane % QF;
+  float* ptr = out_warp + (unsigned long long)sub * row_stride + qbase + ql;
+  uint32_t a = a_stage + (uint32_t)((sub * (QF + 1) + ql) * 4);
+  if (ql < nvalid) {
+#pragma unroll 4
+    for (int c = sub; c < ncols_valid; c += CPI) {
+      *ptr = lds32(a);
+      ptr += CPI * row_stride;
+      a += CPI * (QF + 1) * 4;
     }
   }
   __syncwarp();
@@ -361,18 +396,18 @@ template <int HALF, int CPT, int QF, int LAYOUT>
 __global__ void __launch_bounds__(MAIN_THREADS, (CPT <= 2 ? 3 : 2))
 stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out,
                  unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err) {
-  const StftPlan* P = t.plan;
+  StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
   constexpr int WIN = 2 * HALF;
   constexpr int COLS_W = 32 * CPT;                 // columns per warp
   constexpr int COLS_B = MAIN_THREADS * CPT;       // columns per CTA task
   extern __shared__ __align__(16) float s_main[];
-  float* s_coef = s_main;                                  // [NP_MAX][WIN]
-  float* s_kcb = s_coef + NP_MAX * WIN;                    // [NP_MAX]
-  int* s_qend = reinterpret_cast<int*>(s_kcb + NP_MAX);    // [NP_MAX]
-  float* s_aq = reinterpret_cast<float*>(s_qend + NP_MAX); // [MAX_NQ]
-  float* s_ws = s_aq + MAX_NQ;                             // [WIN]
-  float* s_stage = s_ws + WIN;                             // [warps][COLS_W][QF+1] (time-major layout only)
+  float* s_coef = s_main;                                      // [NP_MAX][WIN]
+  float2* s_meta = reinterpret_cast<float2*>(s_coef + NP_MAX * WIN);   // [NP_MAX] {K*log2(c_p), #queries completed}
+  float* s_aq = reinterpret_cast<float*>(s_meta + NP_MAX);     // [MAX_NQ]
+  float* s_ws = s_aq + MAX_NQ;                                 // [WIN]
+  int* s_task = reinterpret_cast<int*>(s_ws + WIN);            // [4]
+  float* s_stage = reinterpret_cast<float*>(s_task + 4);       // [warps][COLS_W][QF+1] (time-major layout only)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
@@ -381,20 +416,35 @@ stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* _
   const int nq = P->nq, n_chunks = P->n_chunks;
   if (tid < WIN) s_ws[tid] = (float)((double)t.win[tid] / sqrt(P->pmax_raw));
   const unsigned long long n_cblk = (ncl + COLS_B - 1) / COLS_B;
-  const unsigned long long n_tasks = n_cblk * (unsigned long long)n_chunks;
-  float* stage = s_stage + ((LAYOUT == 0) ? warp * COLS_W * (QF + 1) : 0);
+  const long long n_tasks = (long long)(n_cblk * (unsigned long long)n_chunks);
+  const uint32_t a_coef = smem_u32(s_coef), a_meta = smem_u32(s_meta), a_aq = smem_u32(s_aq);
+  const uint32_t a_stage = smem_u32(s_stage) + (uint32_t)((LAYOUT == 0) ? warp * COLS_W * (QF + 1) * 4 : 0);
+  const uint32_t a_st_lane = a_stage + (uint32_t)(lane * (QF + 1) * 4);
 
-  for (unsigned long long task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-    const int ch = (int)(task % (unsigned long long)n_chunks);
-    const unsigned long long cblk = task / (unsigned long long)n_chunks;
+  for (;;) {
+    __syncthreads();   // previous task is done with the tables and with s_task
+    if (tid == 0) s_task[0] = (int)atomicAdd(&P->task_counter, 1u);
+    __syncthreads();
+    const long long task = s_task[0];
+    if (task >= n_tasks) break;
+    const int ch = (int)(task % n_chunks);
+    const unsigned long long cblk = (unsigned long long)(task / n_chunks);
     const int q0 = P->chunk_q0[ch], q1 = P->chunk_q0[ch + 1];
     const int p0 = P->chunk_p0[ch];
     const int p1 = t.qpos[q1 - 1] + 1;
     const int np = p1 - p0 + 1;
-    __syncthreads();   // previous task is done with the tables
     for (int i = tid; i < np * WIN / 4; i += MAIN_THREADS)
       reinterpret_cast<float4*>(s_coef)[i] = reinterpret_cast<const float4*>(t.coef + (size_t)p0 * WIN)[i];
-    for (int i = tid; i < np; i += MAIN_THREADS) { s_kcb[i] = t.kcb[p0 + i]; s_qend[i] = t.qend[p0 + i]; }
+    for (int i = tid; i < np; i += MAIN_THREADS) {
+      int cnt = 0;
+      if (i > 0) {
+        int qa = t.qend[p0 + i - 1], qb = t.qend[p0 + i];
+        qa = qa < q0 ? q0 : qa;
+        qb = qb > q1 ? q1 : qb;
+        cnt = qb > qa ? qb - qa : 0;
+      }
+      s_meta[i] = make_float2(t.kcb[p0 + i], __int_as_float(cnt));
+    }
     for (int i = tid; i < q1 - q0; i += MAIN_THREADS) s_aq[i] = t.aq[q0 + i];
     __syncthreads();
 
@@ -413,24 +463,28 @@ stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* _
         o[c][m] = ylo - yhi;
       }
     }
+    const int ncols_valid = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < (unsigned long long)COLS_W ? (ce - warp_col0) : COLS_W);
+    float* out_warp = out + (warp_col0 - cb) * (unsigned long long)nq;   // time-major
     float prev[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) prev[c] = 0.f;
-    int qi = 0;   // queries of this chunk emitted so far
+    int qrel = 0;               // queries of this chunk emitted so far
+    uint32_t a_cf = a_coef;
 
-    for (int ip = 0; ip < np; ++ip) {
-      const float4* cf = reinterpret_cast<const float4*>(s_coef + ip * WIN);
-      float re[CPT], im[CPT];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) { re[c] = 0.f; im[c] = 0.f; }
+#pragma unroll 1
+    for (int ip = 0; ip < np; ++ip, a_cf += WIN * 4) {
       float cs[WIN];
 #pragma unroll
       for (int v = 0; v < WIN / 4; ++v) {
-        const float4 f = cf[v];
+        const float4 f = lds128(a_cf + 16 * v);
         cs[4 * v] = f.x; cs[4 * v + 1] = f.y; cs[4 * v + 2] = f.z; cs[4 * v + 3] = f.w;
       }
+      const float2 meta = lds64(a_meta + 8 * ip);
+      float re[CPT], im[CPT];
 #pragma unroll
-      for (int m = 0; m < HALF; ++m) {
+      for (int c = 0; c < CPT; ++c) { re[c] = e[c][0] * cs[0]; im[c] = o[c][0] * cs[HALF]; }
+#pragma unroll
+      for (int m = 1; m < HALF; ++m) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           re[c] = fmaf(e[c][m], cs[m], re[c]);
@@ -438,39 +492,31 @@ stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* _
         }
       }
       float db[CPT];
-      const float kc = s_kcb[ip];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) db[c] = fmaf(K_DB, __log2f(fmaf(re[c], re[c], im[c] * im[c])), kc);
-      if (ip > 0) {
-        int qa = s_qend[ip - 1] - q0, qb = s_qend[ip] - q0;
-        qa = qa < 0 ? 0 : qa;
-        qb = qb > (q1 - q0) ? (q1 - q0) : qb;
-        for (int q = qa; q < qb; ++q) {
-          const float a = s_aq[q];
-          if (LAYOUT == 0) {
-            const int slot = q & (QF - 1);
+      for (int c = 0; c < CPT; ++c) db[c] = fmaf(K_DB, lg2_approx(fmaf(re[c], re[c], im[c] * im[c])), meta.x);
+      const int cnt = __float_as_int(meta.y);
+      for (int k = 0; k < cnt; ++k, ++qrel) {
+        const float a = lds32(a_aq + 4 * qrel);
+        if (LAYOUT == 0) {
+          const int slot = qrel & (QF - 1);
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) stage[(c * 32 + lane) * (QF + 1) + slot] = fmaf(a, db[c] - prev[c], prev[c]);
-            if (slot == QF - 1)
-              flush_stage<QF>(stage, COLS_W, warp_col0, ce, cb, out, nq, q0 + (q & ~(QF - 1)), QF, lane);
-          } else {
+          for (int c = 0; c < CPT; ++c) sts32(a_st_lane + (uint32_t)((c * 32 * (QF + 1) + slot) * 4), fmaf(a, db[c] - prev[c], prev[c]));
+          if (slot == QF - 1) flush_stage<QF, COLS_W>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, q0 + qrel - (QF - 1), QF, lane);
+        } else {
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-              const unsigned long long col = warp_col0 + c * 32 + lane;
-              if (col < ce) out[(unsigned long long)(q0 + q) * ld_cols + (col - cb)] = fmaf(a, db[c] - prev[c], prev[c]);
-            }
+          for (int c = 0; c < CPT; ++c) {
+            const unsigned long long col = warp_col0 + c * 32 + lane;
+            if (col < ce) out[(unsigned long long)(q0 + qrel) * ld_cols + (col - cb)] = fmaf(a, db[c] - prev[c], prev[c]);
           }
         }
-        qi = qb;
       }
 #pragma unroll
       for (int c = 0; c < CPT; ++c) prev[c] = db[c];
     }
     if (LAYOUT == 0) {
-      const int rem = (q1 - q0) & (QF - 1);
-      if (rem) flush_stage<QF>(stage, COLS_W, warp_col0, ce, cb, out, nq, q0 + ((q1 - q0) & ~(QF - 1)), rem, lane);
+      const int rem = qrel & (QF - 1);
+      if (rem) flush_stage<QF, COLS_W>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, q0 + qrel - rem, rem, lane);
     }
-    (void)qi;
   }
 }
 
@@ -562,7 +608,7 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float
   const int sms = sm_count();
   if (g.win == 20) {
     constexpr int HALF = 10, CPT = 2, QF = 16;
-    const size_t base = (size_t)(NP_MAX * 2 * HALF + NP_MAX + NP_MAX + MAX_NQ + 2 * HALF) * sizeof(float);
+    const size_t base = (size_t)(NP_MAX * 2 * HALF + 2 * NP_MAX + MAX_NQ + 2 * HALF + 4) * sizeof(float);
     cudaError_t e;
     if (layout == 0) {
       const size_t smem = base + (size_t)(MAIN_THREADS / 32) * 32 * CPT * (QF + 1) * sizeof(float);
