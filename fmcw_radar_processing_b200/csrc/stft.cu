@@ -6,13 +6,14 @@
 //   * the global normalisation max(P) (RP:282-283) is found exactly from per-column bounds.
 // Everything that depends on L (nfft, bins, coefficients, chunks) is planned ON THE DEVICE, so the
 // fused path frames -> compaction -> STFT runs without a host round trip.
+#include <cstdlib>
+
 #include "fmcw_internal.cuh"
 
 namespace fmcw {
 
 constexpr float K_DB = 6.020599913279624f;   // 20*log10(2): psd = 20*log10(P/max) (RP:283)
 constexpr int NP_MAX = 320;                  // bin positions a chunk may hold in shared memory
-constexpr int MAIN_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------
 // plan
@@ -392,8 +393,8 @@ __device__ __forceinline__ void flush_stage(uint32_t a_stage, int ncols_valid, f
   __syncwarp();
 }
 
-template <int HALF, int CPT, int QF, int LAYOUT>
-__global__ void __launch_bounds__(MAIN_THREADS, (CPT <= 2 ? 3 : 2))
+template <int HALF, int CPT, int QF, int LAYOUT, int MAIN_THREADS, int MINB>
+__global__ void __launch_bounds__(MAIN_THREADS, MINB)
 stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out,
                  unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err) {
   StftPlan* P = t.plan;
@@ -602,23 +603,38 @@ cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream
   return cudaGetLastError();
 }
 
+template <int HALF, int CPT, int QF, int THREADS, int MINB>
+static cudaError_t launch_main_variant(const StftTables& t, const StftGeom& g, const float* x, float* out,
+                                       unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
+                                       cudaStream_t st, int sms) {
+  const size_t base = (size_t)(NP_MAX * 2 * HALF + 2 * NP_MAX + MAX_NQ + 2 * HALF + 4) * sizeof(float);
+  cudaError_t e;
+  if (layout == 0) {
+    const size_t smem = base + (size_t)(THREADS / 32) * 32 * CPT * (QF + 1) * sizeof(float);
+    e = cudaFuncSetAttribute(stft_main_kernel<HALF, CPT, QF, 0, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    stft_main_kernel<HALF, CPT, QF, 0, THREADS, MINB><<<sms * MINB, THREADS, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+  } else {
+    e = cudaFuncSetAttribute(stft_main_kernel<HALF, CPT, QF, 1, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+    if (e != cudaSuccess) return e;
+    stft_main_kernel<HALF, CPT, QF, 1, THREADS, MINB><<<sms * MINB, THREADS, base, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
                              cudaStream_t st) {
   const int sms = sm_count();
   if (g.win == 20) {
-    constexpr int HALF = 10, CPT = 2, QF = 16;
-    const size_t base = (size_t)(NP_MAX * 2 * HALF + 2 * NP_MAX + MAX_NQ + 2 * HALF + 4) * sizeof(float);
-    cudaError_t e;
-    if (layout == 0) {
-      const size_t smem = base + (size_t)(MAIN_THREADS / 32) * 32 * CPT * (QF + 1) * sizeof(float);
-      e = cudaFuncSetAttribute(stft_main_kernel<HALF, CPT, QF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      stft_main_kernel<HALF, CPT, QF, 0><<<sms * 3, MAIN_THREADS, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
-    } else {
-      e = cudaFuncSetAttribute(stft_main_kernel<HALF, CPT, QF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-      if (e != cudaSuccess) return e;
-      stft_main_kernel<HALF, CPT, QF, 1><<<sms * 3, MAIN_THREADS, base, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("FMCW_STFT_VARIANT"); variant = v ? atoi(v) : 3; }
+    switch (variant) {
+      case 1: return launch_main_variant<10, 4, 16, 128, 3>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
+      case 2: return launch_main_variant<10, 2, 32, 256, 2>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
+      default: return launch_main_variant<10, 4, 16, 256, 2>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
+      case 4: return launch_main_variant<10, 1, 16, 256, 4>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
+      case 0: return launch_main_variant<10, 2, 16, 256, 3>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
     }
   } else {
     const size_t smem = (size_t)(2 * (g.win / 2)) * 128 * sizeof(float);
