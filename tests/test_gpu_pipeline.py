@@ -1,0 +1,136 @@
+"""GPU tests of the reference-facing surface: radar_processing('no'/'yes') and main() through the JSON
+payloads the dashboard consumes, and the sharded STFT path (emulated ranks on one GPU)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fmcw_radar_processing_b200 import synth
+from fmcw_radar_processing_b200.parse import write_recording
+from oracle import fmcw_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _recording(tmp_path, case):
+    write_recording(str(tmp_path / "radar_data"), case["iq"], case["calib_codes"], case["sxml"])
+
+
+def test_no_branch_payloads_match_oracle(tmp_path):
+    from fmcw_radar_processing_b200.radar_processing import main, uploaded
+    case = H.make_case(n_frames=30, NTS=128, PN=64)
+    case["iq"][[4, 17]] = 2048                     # two frames without a target
+    _recording(tmp_path, case)
+    ref = H.oracle_no(case)
+    del uploaded[:]
+    r = main({"processAnimalActivity": "No", "workdir": str(tmp_path)})        # strcmpi (RP:195)
+    assert r["status"] == "success", r
+    assert [s["step"] for s in r["steps"]] == ["Read Files", "Radar Processing", "Upload JSON"]
+    assert uploaded == ["spectrogram_data.json", "radar_data_range_fft_data.json", "radar_data_range_speed_data.json",
+                        "radar_data_fft_data.json"]
+    sp = json.load(open(tmp_path / "spectrogram_data.json"))
+    assert list(sp) == ["time", "frequency", "intensity", "title", "xLabel", "yLabel"]
+    st = ref["stft"]
+    assert np.allclose(sp["time"], st["T"], rtol=1e-13) and np.allclose(sp["frequency"], st["frequency"], rtol=1e-13)
+    inten = np.array(sp["intensity"], dtype=np.float64)
+    assert inten.shape == st["intensity"].shape == (1024, 28 * 64 - 19)
+    e_db, _ = H.spectrogram_errors(inten, st["intensity"])
+    assert e_db < 1e-3
+    rf = json.load(open(tmp_path / "radar_data_range_fft_data.json"))
+    assert np.allclose(rf["time_axis"], np.arange(30) * 0.15) and np.allclose(rf["array_bin_range"], case["ocfg"].array_bin_range)
+    e_db, _ = H.db_errors(np.array(rf["range_tx1rx1_max_abs"]), ref["range_tx1rx1_max_abs"])
+    assert e_db < 1e-3 and rf["filename"] == "radar_data"
+    rs = json.load(open(tmp_path / "radar_data_range_speed_data.json"))
+    rng = np.array(rs["range"])
+    assert rng.shape == (30, 30)                   # lastDetectedFrame x frame_count (RP:245-250 quirk)
+    assert np.array_equal(rng[:, 0], ref["range"]) and np.count_nonzero(rng[:, 1:]) == 0     # identical bins -> identical metres
+    assert np.array_equal(np.array(rs["speed"])[:, 0], ref["speed"])
+    ff = json.load(open(tmp_path / "radar_data_fft_data.json"))
+    assert ff["frame_index"] == 100 and ff["range_bins"] == list(range(256)) and len(ff["magnitude"]) == 256
+
+
+def test_no_branch_without_any_target_is_a_failed_step(tmp_path):
+    from fmcw_radar_processing_b200.radar_processing import main
+    case = H.make_case(n_frames=3, NTS=64, PN=16)
+    case["iq"][:] = 2048
+    _recording(tmp_path, case)
+    r = main({"processAnimalActivity": "no", "workdir": str(tmp_path)})
+    assert r["status"] == "error" and r["message"] == "Failed at radar processing step."      # RP:276 errors, RPA:56-66
+
+
+def test_other_flag_runs_neither_branch(tmp_path):
+    from fmcw_radar_processing_b200.radar_processing import radar_processing
+    case = H.make_case(n_frames=2, NTS=64, PN=16)
+    _recording(tmp_path, case)
+    assert radar_processing("maybe", workdir=str(tmp_path))["files"] == []
+
+
+def test_yes_branch_batches_match_oracle(tmp_path):
+    from fmcw_radar_processing_b200.radar_processing import radar_processing
+    case = H.make_case(n_frames=520, NTS=64, PN=16)
+    case["iq"][130:180] = 2048                     # a gap inside batch 2
+    _recording(tmp_path, case)
+    frames, n, calib, sx = O.f_parse_data2(case["iq"], case["calib_codes"], case["sxml"])
+    ref = O.radar_processing_yes(frames, calib, sx)
+    r = radar_processing("YES", workdir=str(tmp_path))
+    assert r["files"] == [f"radar_data_spectrogram_batch_{b}.json" for b in (1, 2, 3, 4)]     # RP:443, 587
+    for got, exp in zip(r["batches"], ref["batches"]):
+        assert (got["batch"], got["start_frame"], got["end_frame"]) == (exp["batch"], exp["start_frame"], exp["end_frame"])
+        assert got["intensity"].shape == exp["intensity"].shape
+        e_db, _ = H.spectrogram_errors(got["intensity"], exp["intensity"])
+        assert e_db < 1e-3
+        assert np.allclose(got["T"], exp["T"], rtol=1e-13)
+    assert np.array_equal(np.isnan(r["range"]), np.isnan(ref["range"]))       # NaN fill (RP:524-528); frames > 500 stay 0 (RP:599)
+    assert np.array_equal(np.nan_to_num(r["range"]), np.nan_to_num(ref["range"]))
+    assert np.array_equal(np.nan_to_num(r["speed"]), np.nan_to_num(ref["speed"]))
+    b2 = json.load(open(tmp_path / "radar_data_spectrogram_batch_2.json"))
+    assert b2["title"] == "Spectrogram - Batch 2" and b2["start_frame"] == 101 and b2["end_frame"] == 200
+
+
+@pytest.mark.parametrize("split", [(20, 20), (37, 3), (1, 39), (13, 13, 14)])
+def test_sharded_stft_equals_single_gpu(split):
+    """The C-ABI sharded path (counts -> halo -> local max -> global max -> sharded STFT) with the ranks
+    emulated as handles on one GPU reproduces the single-handle result column for column."""
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    n = sum(split)
+    case = H.make_case(n_frames=n, NTS=128, PN=64)
+    case["iq"][5] = 2048
+    h0 = FmcwCuda(case["cfg"], case["calib"])
+    out0, inten0 = h0.run(case["iq"])
+    info0 = h0.info()
+    win = case["cfg"]["window_length"]
+    hs, Ls, heads = [], [], []
+    f0 = 0
+    for k in split:
+        h = FmcwCuda(case["cfg"], case["calib"])
+        h.process_frames(np.ascontiguousarray(case["iq"][f0:f0 + k]))
+        L = h.info()["L_local"]
+        head = np.zeros(min(L, win - 1), dtype=np.float32)
+        if head.size:
+            h.get_slow_time(head, 0, head.size)
+        hs.append(h); Ls.append(L); heads.append(head)
+        f0 += k
+    L_total = sum(Ls)
+    assert L_total == info0["L_total"]
+    offs = np.concatenate([[0], np.cumsum(Ls)[:-1]]).astype(int)
+    maxes = []
+    for r, h in enumerate(hs):
+        halo = np.concatenate(heads[r + 1:] + [np.zeros(0, np.float32)])[:win - 1].astype(np.float32)
+        h.set_halo(np.ascontiguousarray(halo), halo.size)
+        maxes.append(h.stft_local_max(L_total, int(offs[r])))
+    pmax = max(maxes)
+    assert pmax == pytest.approx(info0["pmax_raw"], rel=1e-6)
+    cols = []
+    for r, h in enumerate(hs):
+        buf = np.empty((max(1, Ls[r]), 1024), dtype=np.float32)
+        h.stft_sharded(L_total, int(offs[r]), info0["pmax_raw"], buf)
+        inf = h.info()
+        assert inf["col_begin"] == sum(c.shape[0] for c in cols)
+        cols.append(buf[:inf["ncol_local"]])
+        h.close()
+    got = np.concatenate(cols)
+    assert got.shape[0] == info0["ncol_total"]
+    assert np.array_equal(got, inten0[:info0["ncol_total"]])
+    h0.close()

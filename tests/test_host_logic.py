@@ -1,0 +1,100 @@
+"""CPU tests of the host-side mirror: configuration (RP:89-179), recording container, payload writers
+(jsonencode conventions) and main()'s error behaviour (RPA:25-66)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fmcw_radar_processing_b200 import payloads as P
+from fmcw_radar_processing_b200 import synth
+from fmcw_radar_processing_b200.config import fmcw_configurations, to_c_config
+from fmcw_radar_processing_b200.parse import f_parse_data2, make_sxml, write_recording
+from oracle import fmcw_oracle as O
+
+
+def test_configuration_matches_oracle_and_reference_names():
+    sx = make_sxml(numSamplesPerChirp=64, numChirpsPerFrame=16, numAntennasRx=2)
+    cfg = fmcw_configurations(sx)
+    o = O.configure(sx)
+    names = ["frame_time", "PRT", "Bandwidth", "num_Tx_antennas", "num_Rx_antennas", "carrier_frequency",
+             "num_ADC_samples_per_chirp", "num_chirps_per_frame", "sampling_frequency", "range_fft_size",
+             "Doppler_fft_size", "IF_scale", "range_threshold", "Doppler_threshold", "min_distance", "max_distance",
+             "max_num_targets", "lambda", "Hz_to_mps_constant", "R_max", "dist_per_bin", "fD_max", "fD_per_bin",
+             "window_length", "max_slider_index", "overlap"]                       # RP:645-672, in order
+    assert list(cfg)[:len(names)] == names
+    for n in names:
+        if n == "max_slider_index":
+            continue
+        assert cfg[n] == getattr(o, "lambda_" if n == "lambda" else n), n
+    c = to_c_config(cfg)
+    assert c.rx_select == 0 and c.window_length == 20 and c.overlap == 19 and c.MAX_FREQ_BINS == 1024
+
+
+def test_recording_round_trip(tmp_path):
+    sx = make_sxml(numSamplesPerChirp=64, numChirpsPerFrame=16, numAntennasRx=2)
+    iq = np.random.default_rng(0).integers(0, 4096, size=(5, 2, 16, 64, 2)).astype(np.int16)
+    calib = synth.default_calib(2, 64)
+    base = str(tmp_path / "radar_data")
+    write_recording(base, iq, calib, sx)
+    frame, n, cal, sx2 = f_parse_data2(base)
+    assert n == 5 and np.array_equal(np.asarray(frame), iq)
+    assert np.allclose(cal, calib / 4095.0)
+    assert fmcw_configurations(sx2) == fmcw_configurations(sx)
+
+
+def test_jsonencode_conventions(tmp_path):
+    path = str(tmp_path / "x.json")
+    P.write_struct(path, [("row", np.arange(3.0)[None, :]), ("col", np.arange(3.0)[:, None]),
+                          ("mat", np.array([[1.0, np.nan], [np.inf, 0.1 + 0.2]])), ("one", np.array([[5.0]])),
+                          ("s", "radar_data"), ("f32", np.float32([0.1, 0.25]))])
+    txt = open(path).read()
+    d = json.loads(txt)
+    assert list(d) == ["row", "col", "mat", "one", "s", "f32"]                   # field order
+    assert d["row"] == [0, 1, 2] and d["col"] == [0, 1, 2]                       # vectors flatten
+    assert d["mat"] == [[1, None], [None, 0.3]]                                  # row-major nesting, NaN/Inf -> null, 15 digits
+    assert d["one"] == 5 and d["s"] == "radar_data"
+    assert '"f32":[0.100000001,0.25]' in txt
+
+
+def test_range_speed_growing_matrix_quirk():
+    """RP:157-159 allocate 1 x N, RP:245-250 write (fr_idx, 1): lastDetectedFrame x N, data in column 1."""
+    vals = np.array([3.0, 0.0, 4.5, 0.0, 0.0])
+    det = np.array([1, 0, 1, 0, 0], dtype=bool)
+    M = P.matlab_growing_matrix(vals, det)
+    assert M.shape == (3, 5) and M[0, 0] == 3.0 and M[2, 0] == 4.5 and M.sum() == 7.5
+    assert P.matlab_growing_matrix(vals, np.zeros(5, bool)).shape == (1, 5)
+    fields = dict(P.range_speed_payload(5, vals, vals, det, "radar_data"))
+    assert np.allclose(fields["time_axis"], np.arange(5) * 0.15) and fields["filename"] == "radar_data"
+
+
+def test_payload_keys_match_reference():
+    keys = lambda f: [k for k, _ in f]
+    assert keys(P.spectrogram_payload([0], [1], np.zeros((2, 2)))) == ["time", "frequency", "intensity", "title", "xLabel", "yLabel"]
+    assert dict(P.spectrogram_payload([0], [1], np.zeros((2, 2))))["title"] == "All Frames - Log-Scaled Spectrogram"
+    assert keys(P.range_fft_payload(2, [0], np.zeros((2, 2)), "f")) == ["time_axis", "array_bin_range", "range_tx1rx1_max_abs", "filename"]
+    assert keys(P.fft_payload(np.zeros(4), "f")) == ["range_bins", "magnitude", "frame_index", "filename"]
+    b = dict(P.batch_spectrogram_payload([0], [1], np.zeros((2, 2)), 3, 201, 300, "radar_data"))
+    assert b["title"] == "Spectrogram - Batch 3" and b["start_frame"] == 201 and b["end_frame"] == 300
+    assert b["xLabel"] == "Time (s) (relative to detected activity)" and b["filename_base"] == "radar_data"
+
+
+def test_main_reports_missing_files_like_the_reference(tmp_path):
+    from fmcw_radar_processing_b200.radar_processing import main
+    r = main({"processAnimalActivity": "no", "workdir": str(tmp_path)})
+    assert r["status"] == "error" and r["message"] == "Failed at reading files from blob storage."
+    assert r["steps"][0]["step"] == "Read Files" and r["steps"][0]["status"] == "error"
+
+
+def test_main_reports_processing_failure_without_gpu(tmp_path):
+    """Without a CUDA device the library refuses to run (no CPU fallback) and main() reports a failed step
+    (RPA:56-66) instead of raising."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fmcw_radar_processing_b200.radar_processing import main
+    sx = make_sxml(numSamplesPerChirp=64, numChirpsPerFrame=16)
+    write_recording(str(tmp_path / "radar_data"), np.full((2, 1, 16, 64, 2), 2048, np.int16), synth.default_calib(1, 64), sx)
+    r = main({"processAnimalActivity": "no", "workdir": str(tmp_path)})
+    assert r["status"] == "error" and r["message"] == "Failed at radar processing step."
+    assert [s["step"] for s in r["steps"]] == ["Read Files", "Radar Processing"]
