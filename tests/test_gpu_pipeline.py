@@ -45,8 +45,9 @@ def test_no_branch_payloads_match_oracle(tmp_path):
     rs = json.load(open(tmp_path / "radar_data_range_speed_data.json"))
     rng = np.array(rs["range"])
     assert rng.shape == (30, 30)                   # lastDetectedFrame x frame_count (RP:245-250 quirk)
-    assert np.array_equal(rng[:, 0], ref["range"]) and np.count_nonzero(rng[:, 1:]) == 0     # identical bins -> identical metres
-    assert np.array_equal(np.array(rs["speed"])[:, 0], ref["speed"])
+    # identical bins -> identical metres / m/s up to jsonencode's 15 significant digits
+    assert np.allclose(rng[:, 0], ref["range"], rtol=1e-14, atol=0) and np.count_nonzero(rng[:, 1:]) == 0
+    assert np.allclose(np.array(rs["speed"])[:, 0], ref["speed"], rtol=1e-14, atol=0)
     ff = json.load(open(tmp_path / "radar_data_fft_data.json"))
     assert ff["frame_index"] == 100 and ff["range_bins"] == list(range(256)) and len(ff["magnitude"]) == 256
 
