@@ -208,7 +208,7 @@ def main():
         if sharded is None:
             h.run(iq, out, inten)
         else:
-            sharded.step(iq, out, inten)
+            sharded.step_async(iq, out, inten)
 
     # ---- device-resident timing: `value` ----
     for _ in range(args.warmup):
@@ -257,8 +257,9 @@ def main():
                 h.run(iq_np, out_np, inten_np)
             else:   # sharded: frames from host, per-rank spectrogram columns back to host
                 iq.copy_(iq_h, non_blocking=True)
-                r = sharded.step(iq, out, inten)
-                inten_h[:max(1, r["ncol_local"])].copy_(inten[:max(1, r["ncol_local"])], non_blocking=True)
+                sharded.step_async(iq, out, inten)
+                ncl_ = h.info()["ncol_local"]
+                inten_h[:max(1, ncl_)].copy_(inten[:max(1, ncl_)], non_blocking=True)
                 for k in out:
                     out_h[k].copy_(out[k], non_blocking=True)
                 torch.cuda.synchronize(dev)

@@ -65,6 +65,9 @@ EXPORTS = {
     "fmcw_set_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "fmcw_stft_local_max": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
     "fmcw_stft_sharded": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.POINTER(fmcw_stft_out)]),
+    "fmcw_shard_pack": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fmcw_shard_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "fmcw_shard_stft": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(fmcw_stft_out)]),
     "fmcw_stft_axes": (C.c_int, [C.POINTER(fmcw_config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmcw_range_spectrum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),

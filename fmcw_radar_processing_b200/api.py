@@ -198,6 +198,18 @@ class FmcwCuda:
         self._check(self.lib.fmcw_stft_sharded(self._h, L_total, sample_offset, pmax_raw, C.byref(so)))
         return intensity
 
+    # ---- asynchronous sharded path (device-side hand-offs) ----
+    def shard_pack(self, msg):
+        self._check(self.lib.fmcw_shard_pack(self._h, _ptr(msg)))
+
+    def shard_plan(self, gathered, world: int, rank: int, local_max):
+        self._check(self.lib.fmcw_shard_plan(self._h, _ptr(gathered), world, rank, _ptr(local_max)))
+
+    def shard_stft(self, global_max, intensity, layout: int = _lib.LAYOUT_TIME_MAJOR):
+        so = self._stft_struct(intensity, layout)
+        self._check(self.lib.fmcw_shard_stft(self._h, _ptr(global_max), C.byref(so)))
+        return intensity
+
     # ---- extras ----
     def range_spectrum(self, iq, frame: int, chirp: int) -> np.ndarray:
         """abs(range_fft(:, chirp)) of one frame (RP:410-411), 0-based indices."""

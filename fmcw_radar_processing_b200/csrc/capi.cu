@@ -135,6 +135,7 @@ struct fmcw_handle {
   StftGeom geom{};
   DevBuf plan, bins, kcb, qpos, aq, qend, coef, swin, hard, derr;
   // scratch
+  DevBuf shard_geom;
   DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, xc, det_list, ndet, inten, synth_tab;
   // state
   uint64_t n_frames = 0;
@@ -471,7 +472,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   ok(h->coef.ensure((size_t)nb_max * 2 * half * 4 + 64));
   h->st.hard_cap = 1u << 20;
   ok(h->hard.ensure((size_t)h->st.hard_cap * 4));
-  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16));
+  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16)); ok(h->shard_geom.ensure(sizeof(ShardGeom)));
   if (e == cudaSuccess) {
     ok(cudaMemsetAsync(h->plan.p, 0, sizeof(StftPlan), h->stream));
     ok(cudaMemsetAsync(h->derr.p, 0, 16, h->stream));
@@ -492,7 +493,7 @@ void fmcw_destroy(fmcw_handle* h) {
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->xc, &h->det_list, &h->ndet, &h->inten,
-                   &h->synth_tab};
+                   &h->synth_tab, &h->shard_geom};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -663,6 +664,55 @@ fmcw_status fmcw_stft_sharded(fmcw_handle* h, uint64_t L_total, uint64_t sample_
   if (h->planned && (h->plan_L != L_total || h->plan_off != sample_offset || h->plan_avail != L + h->halo)) h->planned = false;
   const uint64_t cols = L / h->geom.hop + 1;
   return run_stft(h, false, L_total, sample_offset, L, L + h->halo, false, pmax_raw_global, sout, cols);
+}
+
+// ---- asynchronous sharded path: every hand-off stays on the device --------------------------------
+fmcw_status fmcw_shard_pack(fmcw_handle* h, float* msg_dev) {
+  if (!h || !msg_dev) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  if (!is_device_ptr(msg_dev)) return fail(h, FMCW_ERR_POINTER, "msg must be device memory");
+  CK(launch_shard_pack(h->xc.as<float>(), h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame,
+                       h->cfg.window_length, msg_dev, h->stream), "shard pack kernel");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_shard_plan(fmcw_handle* h, const float* gathered_dev, uint32_t world, uint32_t rank, double* local_max_dev) {
+  if (!h || !gathered_dev || !local_max_dev) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  if (rank >= world) return fail(h, FMCW_ERR_SIZE, "rank >= world");
+  if (!is_device_ptr(gathered_dev) || !is_device_ptr(local_max_dev)) return fail(h, FMCW_ERR_POINTER, "device memory required");
+  CK(launch_shard_layout(gathered_dev, world, rank, h->cfg.window_length, h->xc.as<float>(), h->shard_geom.as<ShardGeom>(),
+                         h->stream), "shard layout kernel");
+  CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
+                      h->shard_geom.as<ShardGeom>()), "stft plan kernel");
+  CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream), "stft max kernels");
+  CK(launch_stft_export_max(h->st, local_max_dev, h->stream), "export max");
+  h->planned = true; h->have_info = false;
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const fmcw_stft_out* sout) {
+  if (!h || !global_max_dev || !sout || !sout->intensity) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done || !h->planned) return fail(h, FMCW_ERR_STATE, "fmcw_shard_plan must run first");
+  if (!is_device_ptr(global_max_dev) || !is_device_ptr(sout->intensity)) return fail(h, FMCW_ERR_POINTER, "device memory required");
+  if (sout->layout > 1) return fail(h, FMCW_ERR_CONFIG, "unknown intensity layout");
+  const uint64_t ld = sout->ld_cols ? sout->ld_cols : sout->capacity_cols;
+  CK(launch_stft_set_max_dev(h->st, global_max_dev, h->stream), "set max");
+  CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
+  CK(launch_stft_main(h->st, h->geom, h->xc.as<float>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
+                      h->derr.as<int>(), h->stream), "stft main kernel");
+  CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
+  h->have_info = false;
+  return FMCW_OK;
 }
 
 fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, uint64_t col_begin, uint64_t ncol, double* time,

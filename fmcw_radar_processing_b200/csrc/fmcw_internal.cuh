@@ -77,10 +77,20 @@ struct StftTables {             // device arrays owned by the handle
 
 struct StftGeom { uint32_t win, hop, nq; double fs; };
 
+// sizes of a sharded run, resolved on the device from the all-gathered shard headers
+struct ShardGeom { unsigned long long L_total, sample_offset, L_local, L_avail; };
+
+
+cudaError_t launch_shard_pack(const float* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, float* msg,
+                              cudaStream_t st);
+cudaError_t launch_shard_layout(const float* gathered, uint32_t world, uint32_t rank, uint32_t win, float* xc,
+                                ShardGeom* geom, cudaStream_t st);
+cudaError_t launch_stft_export_max(const StftTables& t, double* dst, cudaStream_t st);
+cudaError_t launch_stft_set_max_dev(const StftTables& t, const double* src, cudaStream_t st);
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st);
+                             cudaStream_t st, const ShardGeom* d_geom = nullptr);
 cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st);
 cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,

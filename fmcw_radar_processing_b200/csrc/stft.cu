@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          uint32_t PN, unsigned long long L_total_host,
                                                          unsigned long long sample_offset,
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
-                                                         int n_chunks_req) {
+                                                         int n_chunks_req, const ShardGeom* d_geom) {
   __shared__ int s_scan[1024];
   __shared__ int s_wsum[32];
   __shared__ unsigned long long s_nfft;
@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
 
   if (tid == 0) {
     unsigned long long L = L_total_host, Lloc = L_local_host, Lav = L_avail_host;
-    if (d_ndet) { L = *d_ndet * PN; Lloc = L; Lav = L; }
+    if (d_geom) { L = d_geom->L_total; Lloc = d_geom->L_local; Lav = d_geom->L_avail; sample_offset = d_geom->sample_offset; }
+    else if (d_ndet) { L = *d_ndet * PN; Lloc = L; Lav = L; }
     P->L_total = L; P->sample_offset = sample_offset; P->L_avail = Lav;
     P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0; P->task_counter = 0;
     int ok = (L >= (unsigned long long)win) ? 1 : 0;
@@ -573,6 +574,63 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeo
 }
 
 // ------------------------------------------------------------------------------------------------
+// device-side hand-offs of the sharded path (no host round trip between the collectives)
+// ------------------------------------------------------------------------------------------------
+// msg = {L_local & 0xFFFFF, L_local >> 20, first win-1 samples}: the shard header that is all-gathered
+__global__ void shard_pack_kernel(const float* __restrict__ xc, const unsigned long long* __restrict__ d_ndet, uint32_t PN,
+                                  uint32_t win, float* __restrict__ msg) {
+  const unsigned long long L = *d_ndet * PN;
+  const uint32_t i = threadIdx.x;
+  if (i == 0) { msg[0] = (float)(L & 0xFFFFFull); msg[1] = (float)(L >> 20); }
+  if (i < win - 1) msg[2 + i] = (i < L) ? xc[i] : 0.f;
+}
+
+// from the gathered headers: global length, this shard's offset, and the halo (the win-1 samples that
+// follow this shard, possibly spanning several short or empty shards) appended to the local signal
+__global__ void shard_layout_kernel(const float* __restrict__ gathered, uint32_t world, uint32_t rank, uint32_t win,
+                                    float* __restrict__ xc, ShardGeom* __restrict__ geom) {
+  if (threadIdx.x != 0) return;
+  const uint32_t stride = 2 + (win - 1), hw = win - 1;
+  unsigned long long total = 0, off = 0, mine = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    const unsigned long long L = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
+    if (r < rank) off += L;
+    if (r == rank) mine = L;
+    total += L;
+  }
+  uint32_t got = 0;
+  for (uint32_t r = rank + 1; r < world && got < hw; ++r) {
+    const unsigned long long L = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
+    const uint32_t take = (uint32_t)(L < (unsigned long long)(hw - got) ? L : (hw - got));
+    for (uint32_t i = 0; i < take; ++i) xc[mine + got + i] = gathered[r * stride + 2 + i];
+    got += take;
+  }
+  geom->L_total = total; geom->sample_offset = off; geom->L_local = mine; geom->L_avail = mine + got;
+}
+
+__global__ void stft_export_max_kernel(StftTables t, double* dst) { *dst = (t.plan->valid > 0) ? t.plan->pmax_raw : 0.0; }
+__global__ void stft_set_max_dev_kernel(StftTables t, const double* src) { t.plan->pmax_raw = *src; t.plan->task_counter = 0; }
+
+cudaError_t launch_shard_pack(const float* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, float* msg,
+                              cudaStream_t st) {
+  shard_pack_kernel<<<1, 1024, 0, st>>>(xc, d_ndet, PN, win, msg);
+  return cudaGetLastError();
+}
+cudaError_t launch_shard_layout(const float* gathered, uint32_t world, uint32_t rank, uint32_t win, float* xc,
+                                ShardGeom* geom, cudaStream_t st) {
+  shard_layout_kernel<<<1, 32, 0, st>>>(gathered, world, rank, win, xc, geom);
+  return cudaGetLastError();
+}
+cudaError_t launch_stft_export_max(const StftTables& t, double* dst, cudaStream_t st) {
+  stft_export_max_kernel<<<1, 1, 0, st>>>(t, dst);
+  return cudaGetLastError();
+}
+cudaError_t launch_stft_set_max_dev(const StftTables& t, const double* src, cudaStream_t st) {
+  stft_set_max_dev_kernel<<<1, 1, 0, st>>>(t, src);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static int sm_count() {
@@ -584,8 +642,8 @@ static int sm_count() {
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st) {
-  stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks);
+                             cudaStream_t st, const ShardGeom* d_geom) {
+  stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks, d_geom);
   return cudaGetLastError();
 }
 

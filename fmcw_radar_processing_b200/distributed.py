@@ -105,6 +105,44 @@ class ShardedRun:
         self.group = group
         self.frame_counts = frame_counts      # frames per rank (static); gathered once if not given
 
+    def _async_buffers(self, dev):
+        if getattr(self, "_bufs", None) is None:
+            ws = dist.get_world_size(self.group)
+            n = 2 + self.h.cfg["window_length"] - 1
+            self._bufs = dict(msg=torch.zeros(n, dtype=torch.float32, device=dev),
+                              gathered=torch.zeros(ws * n, dtype=torch.float32, device=dev),
+                              gmax=torch.zeros(1, dtype=torch.float64, device=dev),
+                              lib_stream=torch.cuda.ExternalStream(self.h.stream, device=dev))
+        return self._bufs
+
+    def step_async(self, iq, out, intensity, layout=0, gather=True):
+        """Same result as ``step`` with every hand-off in device memory: the host only enqueues kernels and
+        collectives (stream-ordered with events), so the step has no host round trip.  Sizes are read
+        afterwards with ``handle.info()``."""
+        h = self.h
+        dev = iq.device
+        b = self._async_buffers(dev)
+        lib, cur = b["lib_stream"], torch.cuda.current_stream(dev)
+        ws, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        h.process_frames(iq, out)                       # library stream
+        h.shard_pack(b["msg"])
+        cur.wait_stream(lib)
+        dist.all_gather_into_tensor(b["gathered"], b["msg"], group=self.group)          # collective 1
+        lib.wait_stream(cur)
+        h.shard_plan(b["gathered"], ws, rank, b["gmax"])
+        cur.wait_stream(lib)
+        dist.all_reduce(b["gmax"], op=dist.ReduceOp.MAX, group=self.group)              # collective 2
+        lib.wait_stream(cur)
+        h.shard_stft(b["gmax"], intensity, layout)
+        track = None
+        if gather:                                                                       # collective 3
+            if self.frame_counts is None:
+                counts = [None] * ws
+                dist.all_gather_object(counts, int(iq.shape[0]), group=self.group)
+                self.frame_counts = counts
+            track = gather_track(out["range_bin"], out["doppler_bin"], out["range_mag"], self.frame_counts, self.group)
+        return dict(track=track)
+
     def step(self, iq, out, intensity, layout=0, gather=True):
         h = self.h
         dev = iq.device

@@ -165,6 +165,17 @@ FMCW_API fmcw_status fmcw_stft_local_max(fmcw_handle* h, uint64_t L_total, uint6
 FMCW_API fmcw_status fmcw_stft_sharded(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset,
                                        double pmax_raw_global, const fmcw_stft_out* sout);
 
+/* Asynchronous form of the sharded path: every hand-off stays in device memory, the host only enqueues.
+ *   fmcw_process_frames (device buffers) -> fmcw_shard_pack(msg) -> all-gather(msg) -> fmcw_shard_plan(gathered,
+ *   world, rank, local_max) -> all-reduce(max, local_max) -> fmcw_shard_stft(global_max, out).
+ * msg: float[2 + window_length-1] = {L_local & 0xFFFFF, L_local >> 20, first window_length-1 samples};
+ * gathered: the world messages in rank order.  All pointers are device memory; work is queued on the
+ * handle's stream (order it against the collective's stream with events). */
+FMCW_API fmcw_status fmcw_shard_pack(fmcw_handle* h, float* msg_dev);
+FMCW_API fmcw_status fmcw_shard_plan(fmcw_handle* h, const float* gathered_dev, uint32_t world, uint32_t rank,
+                                     double* local_max_dev);
+FMCW_API fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const fmcw_stft_out* sout);
+
 /* Host-side axes in float64: T (RP:276) for columns [col_begin, col_begin+ncol) and
  * log_freq_bins (RP:293-296).  Either pointer may be NULL. */
 FMCW_API fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, uint64_t col_begin, uint64_t ncol,

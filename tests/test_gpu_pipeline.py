@@ -135,3 +135,55 @@ def test_sharded_stft_equals_single_gpu(split):
     assert got.shape[0] == info0["ncol_total"]
     assert np.array_equal(got, inten0[:info0["ncol_total"]])
     h0.close()
+
+
+@pytest.mark.parametrize("split", [(20, 20), (37, 3), (13, 0, 14, 13)])
+def test_async_sharded_path_equals_single_gpu(split):
+    """fmcw_shard_pack / fmcw_shard_plan / fmcw_shard_stft: the device-side hand-offs (headers, halo, offsets,
+    global max) with the all-gather and all-reduce emulated by torch ops on one GPU."""
+    import torch
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    n = sum(split)
+    case = H.make_case(n_frames=n, NTS=128, PN=64)
+    case["iq"][5] = 2048
+    iq_d = torch.from_numpy(case["iq"]).cuda()
+    h0 = FmcwCuda(case["cfg"], case["calib"])
+    out0, inten0 = h0.run(iq_d)
+    info0 = h0.info()
+    win = case["cfg"]["window_length"]
+    world = len(split)
+    hs, msgs, outs = [], [], []
+    f0 = 0
+    for k in split:
+        h = FmcwCuda(case["cfg"], case["calib"])
+        if k:
+            outs.append(h.process_frames(iq_d[f0:f0 + k].contiguous()))
+        else:
+            outs.append(h.process_frames(iq_d[:0].contiguous()))
+        msg = torch.zeros(2 + win - 1, dtype=torch.float32, device="cuda")
+        h.shard_pack(msg)
+        h.synchronize()
+        hs.append(h); msgs.append(msg)
+        f0 += k
+    gathered = torch.cat(msgs).contiguous()
+    maxes = []
+    for r, h in enumerate(hs):
+        m = torch.zeros(1, dtype=torch.float64, device="cuda")
+        h.shard_plan(gathered, world, r, m)
+        h.synchronize()
+        maxes.append(m)
+    gmax = torch.stack(maxes).max().reshape(1).contiguous()
+    assert float(gmax) == pytest.approx(info0["pmax_raw"], rel=1e-6)
+    gmax[0] = info0["pmax_raw"]
+    cols = []
+    for r, h in enumerate(hs):
+        buf = torch.empty((max(1, split[r] * 64), 1024), dtype=torch.float32, device="cuda")
+        h.shard_stft(gmax, buf)
+        inf = h.info()
+        assert inf["L_total"] == info0["L_total"] and inf["col_begin"] == sum(c.shape[0] for c in cols)
+        cols.append(buf[:inf["ncol_local"]].cpu().numpy())
+        h.close()
+    got = np.concatenate(cols)
+    assert got.shape[0] == info0["ncol_total"]
+    assert np.array_equal(got, inten0[:info0["ncol_total"]].cpu().numpy())
+    h0.close()
