@@ -135,7 +135,7 @@ struct fmcw_handle {
   StftGeom geom{};
   DevBuf plan, bins, kcb, qpos, aq, qend, coef, swin, hard, derr;
   // scratch
-  DevBuf shard_geom;
+  DevBuf shard_geom, tcb, tcmeta;
   DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, xc, det_list, ndet, inten, synth_tab;
   // state
   uint64_t n_frames = 0;
@@ -207,6 +207,8 @@ void fill_tables(fmcw_handle* h) {
   h->st.coef = h->coef.as<float>();
   h->st.win = h->swin.as<float>();
   h->st.hard_list = h->hard.as<unsigned int>();
+  h->st.tcB = h->tcb.as<float>();
+  h->st.tc_meta = h->tcmeta.as<float2>();
 }
 
 fmcw_status read_info(fmcw_handle* h) {
@@ -472,6 +474,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   ok(h->coef.ensure((size_t)nb_max * 2 * half * 4 + 64));
   h->st.hard_cap = 1u << 20;
   ok(h->hard.ensure((size_t)h->st.hard_cap * 4));
+  ok(h->tcb.ensure(stft_tc_table_bytes(nb_max) + 256)); ok(h->tcmeta.ensure(stft_tc_meta_bytes(nb_max) + 256));
   ok(h->derr.ensure(16)); ok(h->ndet.ensure(16)); ok(h->shard_geom.ensure(sizeof(ShardGeom)));
   if (e == cudaSuccess) {
     ok(cudaMemsetAsync(h->plan.p, 0, sizeof(StftPlan), h->stream));
@@ -493,7 +496,7 @@ void fmcw_destroy(fmcw_handle* h) {
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->xc, &h->det_list, &h->ndet, &h->inten,
-                   &h->synth_tab, &h->shard_geom};
+                   &h->synth_tab, &h->shard_geom, &h->tcb, &h->tcmeta};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -72,6 +72,8 @@ struct StftTables {             // device arrays owned by the handle
   float* win;                   // [win] kaiser window (host computed, float64 -> float32)
   unsigned int* hard_list;      // columns whose max needs the exhaustive search
   unsigned int hard_cap;
+  float* tcB;                   // tensor-core path: per 128-bin chunk Chi|Clo|Shi|Slo in the UMMA smem layout
+  float2* tc_meta;              // tensor-core path: per bin position {K*log2(c_p), #queries completed}
   int nb_max;
 };
 
@@ -96,6 +98,16 @@ cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout,
                              int* d_err, cudaStream_t st);
+
+// tensor-core (tcgen05) STFT main kernel, window_length = 20 (stft_tc.cu)
+size_t stft_tc_table_bytes(int nb_max);
+size_t stft_tc_meta_bytes(int nb_max);
+cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, float2* tc_meta, int nb_max,
+                                   cudaStream_t st);
+cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const float* x, float* out, const float* tcB,
+                                const float2* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
+                                int layout, int* d_err, cudaStream_t st);
+int stft_variant();            // FMCW_STFT_VARIANT: -1 (default) tensor cores, 0..4 CUDA-core variants
 
 // ---- synthetic scene generator ------------------------------------------------------------------
 cudaError_t launch_synth(const double* tables, uint32_t n_scat, uint64_t seed, uint64_t frame0, uint64_t n_frames,

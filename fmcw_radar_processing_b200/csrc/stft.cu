@@ -639,11 +639,18 @@ static int sm_count() {
   return sms;
 }
 
+int stft_variant() {
+  static int variant = -2;
+  if (variant == -2) { const char* v = getenv("FMCW_STFT_VARIANT"); variant = v ? atoi(v) : -1; }
+  return variant;
+}
+
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
                              cudaStream_t st, const ShardGeom* d_geom) {
   stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks, d_geom);
+  if (g.win == 20 && stft_variant() < 0) return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st);
   return cudaGetLastError();
 }
 
@@ -684,9 +691,10 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
                              cudaStream_t st) {
   const int sms = sm_count();
+  if (g.win == 20 && stft_variant() < 0)
+    return launch_stft_tc_main(t, g, x, out, t.tcB, t.tc_meta, capacity_cols, ld_cols, layout, d_err, st);
   if (g.win == 20) {
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("FMCW_STFT_VARIANT"); variant = v ? atoi(v) : 3; }
+    const int variant = stft_variant();
     switch (variant) {
       case 1: return launch_main_variant<10, 4, 16, 128, 3>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
       case 2: return launch_main_variant<10, 2, 32, 256, 2>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
