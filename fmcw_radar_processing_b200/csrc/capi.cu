@@ -208,7 +208,7 @@ void fill_tables(fmcw_handle* h) {
   h->st.win = h->swin.as<float>();
   h->st.hard_list = h->hard.as<unsigned int>();
   h->st.tcB = h->tcb.as<float>();
-  h->st.tc_meta = h->tcmeta.as<float2>();
+  h->st.tc_meta = h->tcmeta.as<uint32_t>();
 }
 
 fmcw_status read_info(fmcw_handle* h) {

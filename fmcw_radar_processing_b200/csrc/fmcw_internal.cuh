@@ -73,7 +73,7 @@ struct StftTables {             // device arrays owned by the handle
   unsigned int* hard_list;      // columns whose max needs the exhaustive search
   unsigned int hard_cap;
   float* tcB;                   // tensor-core path: per 128-bin chunk Chi|Clo|Shi|Slo in the UMMA smem layout
-  float2* tc_meta;              // tensor-core path: per bin position {K*log2(c_p), #queries completed}
+  uint32_t* tc_meta;            // tensor-core path: per chunk column {doubling flag, first query, #queries}
   int nb_max;
 };
 
@@ -102,10 +102,10 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float
 // tensor-core (tcgen05) STFT main kernel, window_length = 20 (stft_tc.cu)
 size_t stft_tc_table_bytes(int nb_max);
 size_t stft_tc_meta_bytes(int nb_max);
-cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, float2* tc_meta, int nb_max,
+cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t* tc_meta, int nb_max,
                                    cudaStream_t st);
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const float* x, float* out, const float* tcB,
-                                const float2* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
+                                const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st);
 int stft_variant();            // FMCW_STFT_VARIANT: -1 (default) tensor cores, 0..4 CUDA-core variants
 

@@ -5,7 +5,7 @@
 // with E/O the even/odd folded, windowed taps of a spectrogram column.  On the fp32 pipe this costs 20 FMAs
 // per 4-byte output and bounds the kernel at ~50 % FMA-pipe utilisation (profiles/ncu_full_r1b.txt).  Here:
 //   * one CTA tile = 128 spectrogram columns (the M = 128 rows of the UMMA tile, one TMEM lane each);
-//   * bins are walked in chunks of 128 (N = 128): Re and Im accumulators = 256 TMEM columns;
+//   * bins are walked in chunks of 128 (N = 128, one bin of overlap): Re and Im accumulators = 256 TMEM columns;
 //   * operands are split hi + lo in TF32 (cvt.rna) and three products hi*hi + hi*lo + lo*hi are accumulated
 //     in fp32 -- ~2^-22 relative, the float32 class of the CUDA-core kernel (single-pass TF32/BF16 would not
 //     meet the 1e-3 dB tolerance);
@@ -17,8 +17,9 @@
 //     8 rows x 16 bytes); B tiles (planned once on the device) arrive by 1-D bulk copy (cp.async.bulk) on an
 //     mbarrier; tcgen05.commit signals the epilogue, which reads the accumulators with tcgen05.ld, takes
 //     |S|^2 -> lg2 -> dB, runs the interp1 onto the log-frequency axis and writes the spectrogram.
-// Warp roles per CTA (192 threads, two CTAs per SM so that one CTA's MMAs overlap the other's epilogue):
-// warps 0-3 epilogue (thread = column = TMEM lane), warp 4 MMA issuer, warp 5 bulk-copy producer.
+// One CTA per SM (576 threads): warps 0-15 epilogue (lane quarter = warp & 3; the four warps of a quarter each
+// take one 32-bin group of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer.  TMEM (512 columns),
+// the A tiles and the B tiles are double buffered, so the MMAs of chunk c+1 overlap the epilogue of chunk c.
 #include <cstdlib>
 
 #include "fmcw_internal.cuh"
@@ -32,8 +33,12 @@ constexpr int TC_HALF = 10, TC_KP = 16;
 constexpr int TC_M = 128, TC_N = 128;
 constexpr int TC_MAT_BYTES = TC_N * TC_KP * 4;       // 8 KB per operand matrix
 constexpr int TC_B_BYTES = 4 * TC_MAT_BYTES;         // Chi | Clo | Shi | Slo
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_STEP = TC_N - 1;              // new bin positions per chunk (one position of overlap)
 constexpr int TC_QF = 16;
+constexpr int TC_DBS = 129;                     // dB row stride (odd: conflict-free by column and by bin)
+constexpr int TC_SMEM_BAR_OFF = 2 * 4 * TC_MAT_BYTES + 2 * TC_B_BYTES + (MAX_NQ + 32 + MAX_NQ + 32 + 4 * 32 * TC_DBS + 3) / 4 * 4 * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -64,8 +69,8 @@ __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity), "r"(1000000u) : "memory");
   }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t a) {
@@ -101,14 +106,15 @@ __device__ __forceinline__ float lds32(uint32_t a) {
 }
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
-// staged [32 columns][16 queries] tile of one warp -> 64-byte rows of the time-major spectrogram
+// staged [32 columns][16 queries] tile of one warp -> (up to) 64-byte rows of the time-major spectrogram;
+// slots [first, nvalid) of the row are valid
 __device__ __forceinline__ void flush_rows(uint32_t a_stage, int ncols_valid, float* __restrict__ out_warp,
-                                           unsigned long long row_stride, int qbase, int nvalid, int lane) {
+                                           unsigned long long row_stride, int qbase, int first, int nvalid, int lane) {
   __syncwarp();
   const int sub = lane >> 4, ql = lane & 15;
   float* ptr = out_warp + (unsigned long long)sub * row_stride + qbase + ql;
   uint32_t a = a_stage + (uint32_t)((sub * (TC_QF + 1) + ql) * 4);
-  if (ql < nvalid) {
+  if (ql >= first && ql < nvalid) {
 #pragma unroll 4
     for (int c = sub; c < ncols_valid; c += 2) {
       *ptr = lds32(a);
@@ -122,22 +128,25 @@ __device__ __forceinline__ void flush_rows(uint32_t a_stage, int ncols_valid, fl
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// B operands: per chunk of 128 bin positions the matrices Chi | Clo | Shi | Slo in the UMMA layout, and
-// per position {K*log2(c_p), number of log-frequency queries that position completes}
+// B operands: chunk c covers bin positions [c*127, c*127+128) (one position of overlap, so that every chunk
+// carries the bin preceding its first new bin: the lower bracket of the first interp1 interval); per chunk
+// the matrices Chi | Clo | Shi | Slo in the UMMA layout; per position one packed word
+// {bit 31: one-sided doubling, bits 12..23: first query completed by this position, bits 0..11: count}
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, StftGeom g, float* __restrict__ tcB,
-                                                              float2* __restrict__ tc_meta, int n_chunk_cap) {
+                                                              uint32_t* __restrict__ tc_meta, int n_chunk_cap) {
   const StftPlan* P = t.plan;
   if (P->valid <= 0) return;
   const int nb = P->nb;
-  const int n_chunks = (nb + TC_N - 1) / TC_N;
+  const int n_chunks = (nb - 1 + TC_STEP - 1) / TC_STEP;
   if (n_chunks > n_chunk_cap) return;
   const unsigned long long nfft = P->nfft;
   const long long mod = (long long)(2 * nfft);
   const int total = n_chunks * TC_N * TC_KP;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int k = i % TC_KP, pos = i / TC_KP;
-    const int ch = pos / TC_N, n = pos % TC_N;
+    const int k = i % TC_KP, idx = i / TC_KP;
+    const int ch = idx / TC_N, n = idx % TC_N;
+    const int pos = ch * TC_STEP + n;
     double cv = 0.0, sv = 0.0;
     if (pos < nb) {
       const long long bin = t.bins[pos];
@@ -161,175 +170,230 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
     blk[2 * (TC_MAT_BYTES / 4) + off] = shi;
     blk[3 * (TC_MAT_BYTES / 4) + off] = slo;
     if (k == 0) {
-      float kcb = 0.f;
-      int cnt = 0;
+      uint32_t w = 0;
       if (pos < nb) {
-        kcb = t.kcb[pos];
-        if (pos > 0) cnt = t.qend[pos] - t.qend[pos - 1];
+        const int qs = pos > 0 ? t.qend[pos - 1] : 0;
+        const int cnt = pos > 0 ? t.qend[pos] - qs : 0;
+        w = (t.kcb[pos] > 0.f ? 0x80000000u : 0u) | ((uint32_t)qs << 12) | (uint32_t)cnt;
       }
-      tc_meta[pos] = make_float2(kcb, __int_as_float(cnt));
+      tc_meta[idx] = w;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// main kernel
+// main kernel: one CTA per SM, 16 epilogue warps + MMA issuer + bulk-copy producer
 // ------------------------------------------------------------------------------------------------
 template <int LAYOUT>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
-               const float2* __restrict__ tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err) {
+               const uint32_t* __restrict__ tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err,
+               int dbg_mode) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
   extern __shared__ __align__(128) unsigned char smem[];
-  float* sA = reinterpret_cast<float*>(smem);                                   // Ehi | Elo | Ohi | Olo
-  float* sB = reinterpret_cast<float*>(smem + 4 * TC_MAT_BYTES);                // Chi | Clo | Shi | Slo
-  float* s_aq = reinterpret_cast<float*>(smem + 4 * TC_MAT_BYTES + TC_B_BYTES); // [MAX_NQ]
-  float* s_ws = s_aq + MAX_NQ;                                                  // [32]
-  float* s_stage = s_ws + 32;                                                   // [4 warps][32][17]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + 4 * 32 * (TC_QF + 1));
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  float* sA = reinterpret_cast<float*>(smem);                                       // 2 x (Ehi | Elo | Ohi | Olo)
+  float* sB = reinterpret_cast<float*>(smem + 2 * 4 * TC_MAT_BYTES);                // 2 x (Chi | Clo | Shi | Slo)
+  float* s_aq = reinterpret_cast<float*>(smem + 2 * 4 * TC_MAT_BYTES + 2 * TC_B_BYTES);   // [MAX_NQ]
+  float* s_ws = s_aq + MAX_NQ;                                                      // [32]
+  int* s_qpos = reinterpret_cast<int*>(s_ws + 32);                                  // [MAX_NQ] position of each query's lower bracket
+  int* s_qrng = s_qpos + MAX_NQ;                                                    // [32] first query of every chunk
+  float* s_db = reinterpret_cast<float*>(s_qrng + 32);                              // [4 quarters][32 columns][TC_DBS] dB of a chunk
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TC_SMEM_BAR_OFF);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
   const unsigned long long ncl = ce - cb;
   if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
   const int nq = P->nq, nb = P->nb;
-  const int n_chunks = (nb + TC_N - 1) / TC_N;
+  const int n_chunks = (nb - 1 + TC_STEP - 1) / TC_STEP;
   const unsigned long long n_tiles = (ncl + TC_M - 1) / TC_M;
 
-  const uint32_t bar_a = smem_u32(&s_bar[0]), bar_bf = smem_u32(&s_bar[1]), bar_be = smem_u32(&s_bar[2]);
-  const uint32_t bar_tf = smem_u32(&s_bar[3]), bar_te = smem_u32(&s_bar[4]);
+  // barriers: [0,1] a_full, [2,3] a_empty, [4,5] b_full, [6,7] b_empty, [8,9] t_full, [10,11] t_empty
+  const uint32_t bar0 = smem_u32(&s_bar[0]);
+  auto BAR = [&](int i) { return bar0 + (uint32_t)(i * 8); };
   if (tid == 0) {
-    mbar_init(bar_a, 128); mbar_init(bar_bf, 1); mbar_init(bar_be, 1); mbar_init(bar_tf, 1); mbar_init(bar_te, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(0 + i), TC_EPI_WARPS * 32); mbar_init(BAR(2 + i), 1);
+      mbar_init(BAR(4 + i), 1); mbar_init(BAR(6 + i), 1);
+      mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), TC_EPI_WARPS * 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(s_tmem)));
+  if (warp == TC_EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < nq; i += TC_THREADS) s_aq[i] = t.aq[i];
+  for (int i = tid; i < nq; i += TC_THREADS) { s_aq[i] = t.aq[i]; s_qpos[i] = t.qpos[i]; }
+  if (tid <= n_chunks && tid < 32) {   // queries [s_qrng[ch], s_qrng[ch+1]) have their bracket inside chunk ch
+    const int p = tid * TC_STEP;
+    s_qrng[tid] = t.qend[p < nb ? p : nb];
+  }
   if (tid < 2 * TC_HALF) s_ws[tid] = (float)((double)t.win[tid] / sqrt(P->pmax_raw));
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
-    // ===================== epilogue warps: thread = spectrogram column = TMEM lane =====================
-    const uint32_t a_stage = smem_u32(s_stage) + (uint32_t)(warp * 32 * (TC_QF + 1) * 4);
-    const uint32_t a_st_lane = a_stage + (uint32_t)(lane * (TC_QF + 1) * 4);
-    const uint32_t a_aq = smem_u32(s_aq);
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (warp < TC_EPI_WARPS) {
+    // ============ epilogue warps: lane quarter qd = warp & 3 (TMEM lanes 32*qd..), sub-warp sw = warp >> 2 ============
+    const int qd = warp & 3, sw = warp >> 2;
+    const int m = qd * 32 + lane;                         // row of the tile = spectrogram column = TMEM lane
+    const uint32_t a_aq = smem_u32(s_aq), a_qpos = smem_u32(s_qpos);
+    const uint32_t a_db = smem_u32(s_db) + (uint32_t)(qd * 32 * TC_DBS * 4);      // dB rows of this quarter's 32 columns
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
     const float inv = (float)(1.0 / sqrt(P->pmax_raw));
-    uint32_t ph_tf = 0;
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const unsigned long long tile_col0 = cb + tile * TC_M;
-      unsigned long long col = tile_col0 + tid;
+    // the only positions without the one-sided doubling: bin 0 (if planned) and the Nyquist bin
+    const int sp0 = (t.bins[0] == 0) ? 0 : -1;
+    const int sp1 = ((unsigned long long)t.bins[nb - 1] == P->nfft / 2) ? nb - 1 : -1;
+
+    // A operands of one column: mean removed, windowed, folded even/odd, split hi/lo; this warp writes matrix `sw`
+    auto build_a = [&](unsigned long long tile, int buf) {
+      unsigned long long col = cb + tile * TC_M + m;
       if (col >= ce) col = ce - 1;
-      // ---- A operands of this column: mean removed, windowed, folded, split hi/lo ----
-      {
-        const float* xs = x + (col * g.hop - off);
-        float xv[2 * TC_HALF];
-        float mean = 0.f;
+      const float* xs = x + (col * g.hop - off);
+      float xv[2 * TC_HALF];
+      float mean = 0.f;
 #pragma unroll
-        for (int n = 0; n < 2 * TC_HALF; ++n) { xv[n] = __ldg(xs + n); mean += xv[n]; }
-        mean *= (1.0f / (2 * TC_HALF));
-        float ev[TC_KP], ov[TC_KP];
+      for (int n = 0; n < 2 * TC_HALF; ++n) { xv[n] = __ldg(xs + n); mean += xv[n]; }
+      mean *= (1.0f / (2 * TC_HALF));
+      float v[TC_KP];
 #pragma unroll
-        for (int m = 0; m < TC_HALF; ++m) {
-          const float ylo = s_ws[TC_HALF - 1 - m] * (xv[TC_HALF - 1 - m] - mean), yhi = s_ws[TC_HALF + m] * (xv[TC_HALF + m] - mean);
-          ev[m] = ylo + yhi;
-          ov[m] = ylo - yhi;
+      for (int k = 0; k < TC_HALF; ++k) {
+        const float ylo = s_ws[TC_HALF - 1 - k] * (xv[TC_HALF - 1 - k] - mean), yhi = s_ws[TC_HALF + k] * (xv[TC_HALF + k] - mean);
+        v[k] = (sw < 2) ? (ylo + yhi) : (ylo - yhi);
+      }
+      v[TC_HALF] = (sw < 2) ? mean * inv : 0.f;           // DC tap: multiplies the tabulated window response
+#pragma unroll
+      for (int k = TC_HALF + 1; k < TC_KP; ++k) v[k] = 0.f;
+      float* rowp = sA + buf * (4 * TC_MAT_BYTES / 4) + sw * (TC_MAT_BYTES / 4) + (m >> 3) * (TC_KP * 8) + (m & 7) * 4;
+#pragma unroll
+      for (int kc = 0; kc < TC_KP / 4; ++kc) {
+        float4 o4;
+        float* op = &o4.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float hi = tf32_rna(v[4 * kc + j]);
+          op[j] = (sw & 1) ? tf32_rna(v[4 * kc + j] - hi) : hi;
         }
-        ev[TC_HALF] = mean * inv;      // DC tap: multiplies the tabulated window response
-        ov[TC_HALF] = 0.f;
-#pragma unroll
-        for (int m = TC_HALF + 1; m < TC_KP; ++m) { ev[m] = 0.f; ov[m] = 0.f; }
-        float* rowp = sA + (tid >> 3) * (TC_KP * 8) + (tid & 7) * 4;
-#pragma unroll
-        for (int kc = 0; kc < TC_KP / 4; ++kc) {
-          float4 eh, el, oh, ol;
-          float* ehp = &eh.x; float* elp = &el.x; float* ohp = &oh.x; float* olp = &ol.x;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float e = ev[4 * kc + j], o = ov[4 * kc + j];
-            ehp[j] = tf32_rna(e); elp[j] = tf32_rna(e - ehp[j]);
-            ohp[j] = tf32_rna(o); olp[j] = tf32_rna(o - ohp[j]);
-          }
-          *reinterpret_cast<float4*>(rowp + kc * 32) = eh;
-          *reinterpret_cast<float4*>(rowp + (TC_MAT_BYTES / 4) + kc * 32) = el;
-          *reinterpret_cast<float4*>(rowp + 2 * (TC_MAT_BYTES / 4) + kc * 32) = oh;
-          *reinterpret_cast<float4*>(rowp + 3 * (TC_MAT_BYTES / 4) + kc * 32) = ol;
-        }
+        *reinterpret_cast<float4*>(rowp + kc * 32) = o4;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
-      mbar_arrive(bar_a);
+      mbar_arrive(BAR(0 + buf));
+    };
 
-      const unsigned long long warp_col0 = tile_col0 + (unsigned long long)warp * 32;
+    unsigned long long it = 0;                            // local tile counter
+    if (blockIdx.x < n_tiles) build_a(blockIdx.x, 0);
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const unsigned long long next = tile + gridDim.x;
+      if (next < n_tiles) {                               // A of the next tile while this tile's chunks are in flight
+        const int nbuf = (int)((it + 1) & 1);
+        mbar_wait(BAR(2 + nbuf), (uint32_t)((((it + 1) >> 1) & 1) ^ 1));
+        build_a(next, nbuf);
+      }
+      const unsigned long long tile_col0 = cb + tile * TC_M;
+      const unsigned long long warp_col0 = tile_col0 + (unsigned long long)qd * 32;
       const int ncols_valid = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 32ull ? (ce - warp_col0) : 32ull);
-      float* out_warp = out + (warp_col0 - cb) * (unsigned long long)nq;
-      const bool col_ok = (tile_col0 + tid) < ce;
-      float prev = 0.f;
-      int qcur = 0;
+      float* out_warp = out + (warp_col0 - cb) * (unsigned long long)nq;      // time-major rows of this quarter's columns
+      const bool col_ok = (tile_col0 + m) < ce;
       for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(bar_tf, ph_tf);
-        ph_tf ^= 1;
+        const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
+        const int ts = (int)(cseq & 1);
+        const int gi = (sw + ch) & 3;                       // 32-bin group of this chunk converted to dB by this warp
+        const int pos_c0 = ch * TC_STEP;                    // bin position of chunk column 0
+        mbar_wait(BAR(8 + ts), (uint32_t)((cseq >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float2* meta = tc_meta + ch * TC_N;
-#pragma unroll 1
-        for (int g16 = 0; g16 < TC_N / 16; ++g16) {
-          float re[16], im[16];
-          tmem_ld16(t_lane + (uint32_t)(g16 * 16), re);
-          tmem_ld16(t_lane + (uint32_t)(TC_N + g16 * 16), im);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (g16 == TC_N / 16 - 1) {           // accumulators are in registers: hand TMEM back to the MMA warp
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(bar_te);
-          }
+        {
+          float re[32], im[32];
+          const uint32_t c0 = (uint32_t)(ts * 2 * TC_N + gi * 32);
+          float a16[16];
+          tmem_ld16(t_lane + c0, a16);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 mt = __ldg(meta + g16 * 16 + j);
-            const float db = fmaf(K_DB, lg2_approx(fmaf(re[j], re[j], im[j] * im[j])), mt.x);
-            const int cnt = __float_as_int(mt.y);
-            for (int k = 0; k < cnt; ++k, ++qcur) {
-              const float a = lds32(a_aq + 4 * qcur);
-              const float val = fmaf(a, db - prev, prev);
-              if (LAYOUT == 0) {
-                const int slot = qcur & (TC_QF - 1);
-                sts32(a_st_lane + (uint32_t)(slot * 4), val);
-                if (slot == TC_QF - 1) flush_rows(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - (TC_QF - 1), TC_QF, lane);
-              } else {
-                if (col_ok) out[(unsigned long long)qcur * ld_cols + (tile_col0 + tid - cb)] = val;
-              }
-            }
-            prev = db;
+          for (int j = 0; j < 16; ++j) re[j] = a16[j];
+          tmem_ld16(t_lane + c0 + 16, a16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) re[16 + j] = a16[j];
+          tmem_ld16(t_lane + c0 + TC_N, a16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) im[j] = a16[j];
+          tmem_ld16(t_lane + c0 + TC_N + 16, a16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) im[16 + j] = a16[j];
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(BAR(10 + ts));                        // accumulators are in registers: TMEM stage back to the MMA warp
+          if (dbg_mode == 1) { if (re[0] + im[31] == 123.456f) out[0] = 1.f; continue; }
+          // |S|^2 -> dB of 32 bins (independent chains), one-sided doubling for all bins; the (at most two)
+          // un-doubled positions are corrected below
+          const uint32_t a_row = a_db + (uint32_t)((lane * TC_DBS + gi * 32) * 4);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            sts32(a_row + (uint32_t)(j * 4), fmaf(K_DB, lg2_approx(fmaf(re[j], re[j], im[j] * im[j])), K_DB));
+          const int p_lo = pos_c0 + gi * 32;
+          if ((sp0 >= p_lo && sp0 < p_lo + 32) || (sp1 >= p_lo && sp1 < p_lo + 32)) {
+            __syncwarp();
+            const int sp = (sp0 >= p_lo && sp0 < p_lo + 32) ? sp0 : sp1;
+            const uint32_t aa = a_db + (uint32_t)((lane * TC_DBS + (sp - pos_c0)) * 4);
+            sts32(aa, lds32(aa) - K_DB);
           }
         }
-      }
-      if (LAYOUT == 0) {
-        const int rem = qcur & (TC_QF - 1);
-        if (rem) flush_rows(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - rem, rem, lane);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");        // the quarter's 128 dB values per column are complete
+        // ---- interp1 onto the log-frequency axis: queries whose bracket lies in this chunk, in blocks of 32 ----
+        const int Qa = s_qrng[ch], Qb = s_qrng[ch + 1];
+        for (int b = (Qa >> 5) + ((sw - (Qa >> 5) - ch) & 3); b * 32 < Qb; b += 4) {
+          if (LAYOUT == 0) {
+            // lanes = 32 consecutive queries: coalesced 128-byte rows, no staging
+            const int q = b * 32 + lane;
+            const bool ok = q >= Qa && q < Qb;
+            const int jl = ok ? __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0 : 0;
+            const float a = lds32(a_aq + 4 * q);
+            uint32_t ad = a_db + (uint32_t)(jl * 4);
+            float* ptr = out_warp + q;
+            if (ok) {
+#pragma unroll 4
+              for (int c = 0; c < ncols_valid; ++c) {
+                const float lo = lds32(ad), hi = lds32(ad + 4);
+                *ptr = fmaf(a, hi - lo, lo);
+                ptr += nq;
+                ad += TC_DBS * 4;
+              }
+            }
+          } else {
+            // lanes = columns: coalesced rows of the frequency-major layout
+            const int q0 = max(Qa, b * 32), q1 = min(Qb, b * 32 + 32);
+            const uint32_t ad = a_db + (uint32_t)(lane * TC_DBS * 4);
+            for (int q = q0; q < q1; ++q) {
+              const int jq = __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0;
+              const float a = lds32(a_aq + 4 * q);
+              const float lo = lds32(ad + (uint32_t)(jq * 4)), hi = lds32(ad + (uint32_t)(jq * 4 + 4));
+              if (col_ok) out[(unsigned long long)q * ld_cols + (tile_col0 + m - cb)] = fmaf(a, hi - lo, lo);
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");        // dB rows may be overwritten by the next chunk
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_EPI_WARPS) {
     // ===================== MMA issuer: one thread drives the tensor core =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-      const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
-      uint32_t ph_a = 0, ph_bf = 0, ph_te = 0;
-      for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        mbar_wait(bar_a, ph_a);
-        ph_a ^= 1;
+      unsigned long long it = 0;
+      for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int abuf = (int)(it & 1);
+        mbar_wait(BAR(0 + abuf), (uint32_t)((it >> 1) & 1));
+        const uint32_t aA = smem_u32(sA) + (uint32_t)(abuf * 4 * TC_MAT_BYTES);
         for (int ch = 0; ch < n_chunks; ++ch) {
-          mbar_wait(bar_bf, ph_bf);
-          ph_bf ^= 1;
-          mbar_wait(bar_te, ph_te ^ 1);      // TMEM free (passes immediately the first time)
-          ph_te ^= 1;
+          const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
+          const int st = (int)(cseq & 1);
+          const uint32_t par = (uint32_t)((cseq >> 1) & 1);
+          mbar_wait(BAR(4 + st), par);               // B tile landed
+          mbar_wait(BAR(10 + st), par ^ 1);          // TMEM stage drained (passes immediately the first two times)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t aB = smem_u32(sB) + (uint32_t)(st * TC_B_BYTES);
 #pragma unroll
           for (int part = 0; part < 2; ++part) {          // 0: Re = E * C^T, 1: Im = O * S^T
-            const uint32_t d = tmem_base + (uint32_t)(part * TC_N);
+            const uint32_t d = tmem_base + (uint32_t)(st * 2 * TC_N + part * TC_N);
             const uint32_t a_hi = aA + (uint32_t)((2 * part) * TC_MAT_BYTES), a_lo = a_hi + TC_MAT_BYTES;
             const uint32_t b_hi = aB + (uint32_t)((2 * part) * TC_MAT_BYTES), b_lo = b_hi + TC_MAT_BYTES;
 #pragma unroll
@@ -340,23 +404,24 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
               umma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), idesc, 1u);
             }
           }
-          umma_commit(bar_be);     // B tile consumed
-          umma_commit(bar_tf);     // accumulators ready
+          umma_commit(BAR(6 + st));                    // B stage consumed
+          umma_commit(BAR(8 + st));                    // accumulators ready
         }
+        umma_commit(BAR(2 + abuf));                    // A buffer consumed
       }
     }
     __syncwarp();
   } else {
     // ===================== producer: B tiles by 1-D bulk copy =====================
     if (lane == 0) {
-      uint32_t ph_be = 0;
-      const uint32_t aB = smem_u32(sB);
-      for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      unsigned long long it = 0;
+      for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         for (int ch = 0; ch < n_chunks; ++ch) {
-          mbar_wait(bar_be, ph_be ^ 1);
-          ph_be ^= 1;
-          mbar_expect_tx(bar_bf, TC_B_BYTES);
-          bulk_g2s(aB, tcB + (size_t)ch * (TC_B_BYTES / 4), TC_B_BYTES, bar_bf);
+          const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
+          const int st = (int)(cseq & 1);
+          mbar_wait(BAR(6 + st), (uint32_t)(((cseq >> 1) & 1) ^ 1));
+          mbar_expect_tx(BAR(4 + st), TC_B_BYTES);
+          bulk_g2s(smem_u32(sB) + (uint32_t)(st * TC_B_BYTES), tcB + (size_t)ch * (TC_B_BYTES / 4), TC_B_BYTES, BAR(4 + st));
         }
       }
     }
@@ -364,40 +429,42 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+  if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
 size_t stft_tc_table_bytes(int nb_max) {
-  const int n_chunks = (nb_max + TC_N - 1) / TC_N;
+  const int n_chunks = (nb_max - 1 + TC_STEP - 1) / TC_STEP + 1;
   return (size_t)n_chunks * TC_B_BYTES;
 }
 size_t stft_tc_meta_bytes(int nb_max) {
-  const int n_chunks = (nb_max + TC_N - 1) / TC_N;
-  return (size_t)n_chunks * TC_N * sizeof(float2);
+  const int n_chunks = (nb_max - 1 + TC_STEP - 1) / TC_STEP + 1;
+  return (size_t)n_chunks * TC_N * sizeof(uint32_t);
 }
 
-cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, float2* tc_meta, int nb_max,
+cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t* tc_meta, int nb_max,
                                    cudaStream_t st) {
-  const int n_chunk_cap = (nb_max + TC_N - 1) / TC_N;
+  const int n_chunk_cap = (nb_max - 1 + TC_STEP - 1) / TC_STEP + 1;
   stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, tc_meta, n_chunk_cap);
   return cudaGetLastError();
 }
 
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const float* x, float* out, const float* tcB,
-                                const float2* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
+                                const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const size_t smem = 4 * TC_MAT_BYTES + TC_B_BYTES + (MAX_NQ + 32 + 4 * 32 * (TC_QF + 1)) * sizeof(float) + 8 * 8 + 16;
+  const size_t smem = TC_SMEM_BAR_OFF + 16 * 8 + 16;
+  static int dbg = -1;
+  if (dbg < 0) { const char* v = getenv("FMCW_TC_DEBUG"); dbg = v ? atoi(v) : 0; }
   cudaError_t e;
   if (layout == 0) {
     e = cudaFuncSetAttribute(stft_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    stft_tc_kernel<0><<<sms * 2, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err);
+    stft_tc_kernel<0><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg);
   } else {
     e = cudaFuncSetAttribute(stft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    stft_tc_kernel<1><<<sms * 2, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err);
+    stft_tc_kernel<1><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg);
   }
   return cudaGetLastError();
 }
