@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
 // ------------------------------------------------------------------------------------------------
 // main kernel: one CTA per SM, 16 epilogue warps + MMA issuer + bulk-copy producer
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT>
+template <int LAYOUT, int NQC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
                const uint32_t* __restrict__ tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err,
@@ -341,26 +341,36 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
         asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");        // the quarter's 128 dB values per column are complete
         // ---- interp1 onto the log-frequency axis: queries whose bracket lies in this chunk, in blocks of 32 ----
         const int Qa = s_qrng[ch], Qb = s_qrng[ch + 1];
-        for (int b = (Qa >> 5) + ((sw - (Qa >> 5) - ch) & 3); b * 32 < Qb; b += 4) {
-          if (LAYOUT == 0) {
-            // lanes = 32 consecutive queries: coalesced 128-byte rows, no staging
+        if (LAYOUT == 0) {
+          // lanes = 32 consecutive queries (coalesced 128-byte rows, no staging); the four warps of a quarter
+          // split its 32 columns, so the work is balanced whatever the number of query blocks
+          const int c_lo = sw * 8;
+          for (int b = Qa >> 5; b * 32 < Qb; ++b) {
             const int q = b * 32 + lane;
             const bool ok = q >= Qa && q < Qb;
             const int jl = ok ? __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0 : 0;
             const float a = lds32(a_aq + 4 * q);
-            uint32_t ad = a_db + (uint32_t)(jl * 4);
-            float* ptr = out_warp + q;
-            if (ok) {
-#pragma unroll 4
-              for (int c = 0; c < ncols_valid; ++c) {
-                const float lo = lds32(ad), hi = lds32(ad + 4);
-                *ptr = fmaf(a, hi - lo, lo);
-                ptr += nq;
-                ad += TC_DBS * 4;
+            const uint32_t ad = a_db + (uint32_t)((c_lo * TC_DBS + jl) * 4);
+            if (NQC > 0 && ncols_valid == 32) {
+              float* ptr = out_warp + (unsigned long long)c_lo * NQC + q;
+              float lo[8], hi[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) { lo[c] = lds32(ad + (uint32_t)(c * TC_DBS * 4)); hi[c] = lds32(ad + (uint32_t)(c * TC_DBS * 4 + 4)); }
+              if (ok) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ptr[c * NQC] = fmaf(a, hi[c] - lo[c], lo[c]);
+              }
+            } else if (ok) {
+              float* ptr = out_warp + (unsigned long long)c_lo * nq + q;
+              for (int c = 0; c < 8 && c_lo + c < ncols_valid; ++c) {
+                const float lo = lds32(ad + (uint32_t)(c * TC_DBS * 4)), hi = lds32(ad + (uint32_t)(c * TC_DBS * 4 + 4));
+                ptr[(unsigned long long)c * nq] = fmaf(a, hi - lo, lo);
               }
             }
-          } else {
-            // lanes = columns: coalesced rows of the frequency-major layout
+          }
+        } else {
+          // lanes = columns: coalesced rows of the frequency-major layout; query blocks are dealt to the four warps
+          for (int b = (Qa >> 5) + ((sw - (Qa >> 5) - ch) & 3); b * 32 < Qb; b += 4) {
             const int q0 = max(Qa, b * 32), q1 = min(Qb, b * 32 + 32);
             const uint32_t ad = a_db + (uint32_t)(lane * TC_DBS * 4);
             for (int q = q0; q < q1; ++q) {
@@ -456,16 +466,20 @@ cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const fl
   const size_t smem = TC_SMEM_BAR_OFF + 16 * 8 + 16;
   static int dbg = -1;
   if (dbg < 0) { const char* v = getenv("FMCW_TC_DEBUG"); dbg = v ? atoi(v) : 0; }
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+#define FMCW_TC_LAUNCH(L, Q)                                                                                       \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(stft_tc_kernel<L, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    if (e != cudaSuccess) return e;                                                                                \
+    stft_tc_kernel<L, Q><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg); \
+  } while (0)
   if (layout == 0) {
-    e = cudaFuncSetAttribute(stft_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    stft_tc_kernel<0><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg);
+    if (g.nq == 1024) FMCW_TC_LAUNCH(0, 1024);
+    else FMCW_TC_LAUNCH(0, 0);
   } else {
-    e = cudaFuncSetAttribute(stft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    stft_tc_kernel<1><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg);
+    FMCW_TC_LAUNCH(1, 0);
   }
+#undef FMCW_TC_LAUNCH
   return cudaGetLastError();
 }
 
