@@ -135,7 +135,7 @@ struct fmcw_handle {
   StftGeom geom{};
   DevBuf plan, bins, kcb, qpos, aq, qend, coef, swin, hard, derr;
   // scratch
-  DevBuf shard_geom, tcb, tcmeta;
+  DevBuf shard_geom, tcb, tcmeta, colub;
   DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, xc, det_list, ndet, inten, synth_tab;
   // state
   uint64_t n_frames = 0;
@@ -274,6 +274,8 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   CK(pick(out ? out->slow_time_mag : nullptr, h->o_slow, nf * PN * 4, true, t), "alloc"); d.slow = (float*)t;
   CK(h->det_list.ensure(nf * 4), "alloc det_list");
   CK(h->xc.ensure((nf * PN + c.window_length) * 4), "alloc slow-time signal");
+  CK(h->colub.ensure((nf * PN + c.window_length) * 4), "alloc column bounds");
+  h->st.col_ub = h->colub.as<float>();
 
   ChainParams p{};
   p.iq = d_iq; p.n_frames = n_frames; p.NTS = NTS; p.PN = PN; p.n_rx = n_rx; p.rx_sel = rx_sel; p.ND = ND;
@@ -496,7 +498,7 @@ void fmcw_destroy(fmcw_handle* h) {
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->xc, &h->det_list, &h->ndet, &h->inten,
-                   &h->synth_tab, &h->shard_geom, &h->tcb, &h->tcmeta};
+                   &h->synth_tab, &h->shard_geom, &h->tcb, &h->tcmeta, &h->colub};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -594,6 +596,8 @@ fmcw_status fmcw_stft(fmcw_handle* h, const float* x, uint64_t L, const fmcw_stf
   cudaSetDevice(h->device);
   if (L < h->cfg.window_length) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length samples");
   CK(h->xc.ensure((L + h->cfg.window_length) * 4), "alloc signal");
+  CK(h->colub.ensure((L + h->cfg.window_length) * 4), "alloc column bounds");
+  h->st.col_ub = h->colub.as<float>();
   CK(cudaMemcpyAsync(h->xc.p, x, L * 4, is_device_ptr(x) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream),
      "copy signal");
   h->frames_done = false; h->planned = false; h->halo = 0; h->n_frames = 0;

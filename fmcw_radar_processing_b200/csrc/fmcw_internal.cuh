@@ -72,6 +72,7 @@ struct StftTables {             // device arrays owned by the handle
   float* win;                   // [win] kaiser window (host computed, float64 -> float32)
   unsigned int* hard_list;      // columns whose max needs the exhaustive search
   unsigned int hard_cap;
+  float* col_ub;                // [local columns] trivial upper bound 2*(sum|y|)^2 of each column's maximum
   float* tcB;                   // tensor-core path: per 128-bin chunk Chi|Clo|Shi|Slo in the UMMA smem layout
   uint32_t* tc_meta;            // tensor-core path: per chunk column {doubling flag, first query, #queries}
   int nb_max;

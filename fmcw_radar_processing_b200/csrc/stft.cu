@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          uint32_t PN, unsigned long long L_total_host,
                                                          unsigned long long sample_offset,
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
-                                                         int n_chunks_req, const ShardGeom* d_geom) {
+                                                         int n_chunks_req, const ShardGeom* d_geom, int coef_rows) {
   __shared__ int s_scan[1024];
   __shared__ int s_wsum[32];
   __shared__ unsigned long long s_nfft;
@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
   const int half = win / 2;
   const int odd = win & 1;
   const long long mod = (long long)(2 * nfft);
-  for (int i = tid; i < nb * half; i += blockDim.x) {
+  // (the tensor-core path tabulates its own operands and only needs the rows of bins 0/1 here)
+  const int n_rows = (coef_rows > 0 && coef_rows < nb) ? coef_rows : nb;
+  for (int i = tid; i < n_rows * half; i += blockDim.x) {
     const int p = i / half, m = i - p * half;
     const long long bin = t.bins[p];
     const long long twod = odd ? (2 * m + 2) : (2 * m + 1);       // 2*delta, delta = tap distance from the centre
@@ -191,18 +193,20 @@ __global__ void __launch_bounds__(256) stft_colstat_kernel(StftTables t, StftGeo
   for (unsigned long long col = cb + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; col < ce;
        col += (unsigned long long)gridDim.x * blockDim.x) {
     const float* xs = x + (col * g.hop - off);
-    float s0 = 0.f, re = 0.f, im = 0.f;
+    float s0 = 0.f, re = 0.f, im = 0.f, sabs = 0.f;
     const int cidx = half;   // centre tap for odd windows
     for (int m = 0; m < half; ++m) {
       const int lo = odd ? (cidx - 1 - m) : (half - 1 - m), hi = odd ? (cidx + 1 + m) : (half + m);
       const float ylo = s_w[lo] * xs[lo], yhi = s_w[hi] * xs[hi];
       s0 += ylo + yhi;
+      sabs += fabsf(ylo) + fabsf(yhi);
       re = fmaf(ylo + yhi, s_c1[m], re);
       im = fmaf(ylo - yhi, s_c1[half + m], im);
     }
-    if (odd) { const float yc = s_w[cidx] * xs[cidx]; s0 += yc; re += yc; }
+    if (odd) { const float yc = s_w[cidx] * xs[cidx]; s0 += yc; re += yc; sabs += fabsf(yc); }
     const float lb = fmaxf(s0 * s0, c1 * fmaf(re, re, im * im));
     best = fmaxf(best, lb);
+    t.col_ub[col - cb] = 2.f * sabs * sabs;          // trivial upper bound of this column's maximum
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, m));
@@ -233,17 +237,16 @@ __global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom
   for (unsigned long long col0 = first - lane; col0 < ce; col0 += stride) {
     const unsigned long long col = col0 + lane;
     bool cand = false, nonneg = true;
-    float sabs = 0.f, dl = 0.f;
-    if (col < ce) {
+    float dl = 0.f;
+    if (col < ce && t.col_ub[col - cb] > lb) {         // only columns whose trivial bound beats the lower bound
       const float* xs = x + (col * g.hop - off);
       const float c0 = 0.5f * (float)(win - 1);
       for (int n = 0; n < win; ++n) {
         const float y = s_w[n] * xs[n];
         nonneg = nonneg && (y >= 0.f);
-        sabs += fabsf(y);
         dl = fmaf(fabsf((float)n - c0), fabsf(y), dl);
       }
-      cand = 2.f * sabs * sabs > lb;
+      cand = true;
     }
     unsigned mask = __ballot_sync(0xffffffffu, cand);
     while (mask) {
@@ -649,8 +652,10 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
                              cudaStream_t st, const ShardGeom* d_geom) {
-  stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks, d_geom);
-  if (g.win == 20 && stft_variant() < 0) return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st);
+  const bool tc = (g.win == 20 && stft_variant() < 0);
+  stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks, d_geom,
+                                       tc ? 2 : 0);
+  if (tc) return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st);
   return cudaGetLastError();
 }
 
