@@ -115,6 +115,23 @@ class ShardedRun:
                               lib_stream=torch.cuda.ExternalStream(self.h.stream, device=dev))
         return self._bufs
 
+    def _gather_track_async(self, out, dev):
+        """Collective 3 without host work: one stack kernel into a preallocated message, one all-gather.
+        Returns [world, 3, n_max] float32 (range bin, Doppler bin, strength); rows past a rank's frame count
+        are padding."""
+        ws = dist.get_world_size(self.group)
+        n = int(out["range_bin"].shape[0])
+        tb = getattr(self, "_track_bufs", None)
+        if tb is None or tb[0].shape[1] != n:
+            tb = (torch.empty(3, n, dtype=torch.float32, device=dev), torch.empty(ws, 3, n, dtype=torch.float32, device=dev))
+            self._track_bufs = tb
+        msg, gathered = tb
+        msg[0].copy_(out["range_bin"])
+        msg[1].copy_(out["doppler_bin"])
+        msg[2].copy_(out["range_mag"])
+        dist.all_gather_into_tensor(gathered, msg, group=self.group)
+        return gathered
+
     def step_async(self, iq, out, intensity, layout=0, gather=True):
         """Same result as ``step`` with every hand-off in device memory: the host only enqueues kernels and
         collectives (stream-ordered with events), so the step has no host round trip.  Sizes are read
@@ -130,17 +147,11 @@ class ShardedRun:
         dist.all_gather_into_tensor(b["gathered"], b["msg"], group=self.group)          # collective 1
         lib.wait_stream(cur)
         h.shard_plan(b["gathered"], ws, rank, b["gmax"])
+        track = self._gather_track_async(out, dev) if gather else None                   # collective 3 (overlaps plan/max)
         cur.wait_stream(lib)
         dist.all_reduce(b["gmax"], op=dist.ReduceOp.MAX, group=self.group)              # collective 2
         lib.wait_stream(cur)
         h.shard_stft(b["gmax"], intensity, layout)
-        track = None
-        if gather:                                                                       # collective 3
-            if self.frame_counts is None:
-                counts = [None] * ws
-                dist.all_gather_object(counts, int(iq.shape[0]), group=self.group)
-                self.frame_counts = counts
-            track = gather_track(out["range_bin"], out["doppler_bin"], out["range_mag"], self.frame_counts, self.group)
         return dict(track=track)
 
     def step(self, iq, out, intensity, layout=0, gather=True):
