@@ -37,7 +37,7 @@ constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr int TC_STEP = TC_N - 1;              // new bin positions per chunk (one position of overlap)
 constexpr int TC_QF = 16;
-constexpr int TC_DBS = 129;                     // dB row stride (odd: conflict-free by column and by bin)
+constexpr int TC_DBS = 130;                     // dB row stride: 8-byte aligned rows, conflict-free 64-bit column-wise stores
 constexpr int TC_SMEM_BAR_OFF = 2 * 4 * TC_MAT_BYTES + 2 * TC_B_BYTES + (MAX_NQ + 32 + MAX_NQ + 32 + 4 * 32 * TC_DBS + 3) / 4 * 4 * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,6 +103,20 @@ __device__ __forceinline__ float lds32(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory"); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return r;
 }
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
@@ -327,9 +341,14 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
           // |S|^2 -> dB of 32 bins (independent chains), one-sided doubling for all bins; the (at most two)
           // un-doubled positions are corrected below
           const uint32_t a_row = a_db + (uint32_t)((lane * TC_DBS + gi * 32) * 4);
+          const float2 kk = make_float2(K_DB, K_DB);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            sts32(a_row + (uint32_t)(j * 4), fmaf(K_DB, lg2_approx(fmaf(re[j], re[j], im[j] * im[j])), K_DB));
+          for (int j = 0; j < 32; j += 2) {                 // two bins per packed instruction (FMUL2 / FFMA2)
+            const float2 r2 = make_float2(re[j], re[j + 1]), i2 = make_float2(im[j], im[j + 1]);
+            const float2 p2 = fma2(r2, r2, mul2(i2, i2));
+            const float2 l2 = make_float2(lg2_approx(p2.x), lg2_approx(p2.y));
+            sts64(a_row + (uint32_t)(j * 4), fma2(kk, l2, kk));
+          }
           const int p_lo = pos_c0 + gi * 32;
           if ((sp0 >= p_lo && sp0 < p_lo + 32) || (sp1 >= p_lo && sp1 < p_lo + 32)) {
             __syncwarp();
