@@ -30,7 +30,7 @@ UNIT = "frames/s"
 # algorithmic bytes per frame of the C1/C2 shape (1 processed RX, 64 x 128, hop 1)
 CHAIN_BYTES_PER_FRAME = 128 * 64 * 4 + 256 * 4 + 16 + 16 * 4 + 64 * 4          # 34,128
 STFT_BYTES_PER_FRAME = 64 * 4 + 64 * 1024 * 4                                  # 262,400
-KERNELS_PER_STEP = 9   # frame_chain, scan_flags, gather_rows, stft_plan, colstat, refine, hard, finalize, stft_main
+KERNELS_PER_STEP = 10  # frame_chain, scan_flags, gather_rows, stft_plan, stft_tc_prepare, colstat, refine, hard, finalize, stft_tc
 
 
 def build_workload(n_frames, n_rx=3):
@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=5000)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=400, help="frames of the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=4000, help="frames of the bounded cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=2000, help="frames per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -303,7 +303,7 @@ def main():
     ncl, L_local = info["ncol_local"], info["L_local"]
     stft_bytes = L_local * 4 + ncl * 1024 * 4
     achieved = stft_bytes / (stage_ms[3] * 1e-3) / 1e9 if stage_ms[3] > 0 else None
-    roofline = {"kernel": "stft_main_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "stft_tc_kernel (tcgen05 STFT main)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(stft_bytes), "avg_launch_ms": float(stage_ms[3]),
                 "stage_ms": {"frame_chain": float(stage_ms[0]), "compaction": float(stage_ms[1]),
@@ -312,7 +312,7 @@ def main():
                              (total_frames * (CHAIN_BYTES_PER_FRAME + STFT_BYTES_PER_FRAME) / world / (dev_ms * 1e-3) / 1e9),
                 "chain_frac_of_peak": None}
     roofline["chain_frac_of_peak"] = roofline["chain_gbs"] / peak
-    traffic_path = os.path.join(ROOT, "profiles", "stft_main_traffic.json")
+    traffic_path = os.path.join(ROOT, "profiles", "stft_tc_traffic.json")
     if os.path.exists(traffic_path):
         roofline["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
 

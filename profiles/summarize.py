@@ -60,7 +60,7 @@ def main():
         for k in KEYS:
             if k in d:
                 lines.append(f"   {k:75s} {d[k]}")
-    for pat in ("stft_main", "frame_chain"):
+    for pat in ("stft_tc_kernel", "stft_main", "frame_chain"):
         m = source_mix(rep, pat)
         if m:
             tot, c, smp = m
