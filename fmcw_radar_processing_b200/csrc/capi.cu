@@ -694,12 +694,9 @@ fmcw_status fmcw_shard_plan(fmcw_handle* h, const float* gathered_dev, uint32_t 
   if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
   if (rank >= world) return fail(h, FMCW_ERR_SIZE, "rank >= world");
   if (!is_device_ptr(gathered_dev) || !is_device_ptr(local_max_dev)) return fail(h, FMCW_ERR_POINTER, "device memory required");
-  CK(launch_shard_layout(gathered_dev, world, rank, h->cfg.window_length, h->xc.as<float>(), h->shard_geom.as<ShardGeom>(),
-                         h->stream), "shard layout kernel");
   CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
-                      h->shard_geom.as<ShardGeom>()), "stft plan kernel");
-  CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream), "stft max kernels");
-  CK(launch_stft_export_max(h->st, local_max_dev, h->stream), "export max");
+                      gathered_dev, world, rank, h->xc.as<float>()), "stft plan kernel");
+  CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream, local_max_dev), "stft max kernels");
   h->planned = true; h->have_info = false;
   return FMCW_OK;
 }
@@ -713,10 +710,9 @@ fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const 
   if (!is_device_ptr(global_max_dev) || !is_device_ptr(sout->intensity)) return fail(h, FMCW_ERR_POINTER, "device memory required");
   if (sout->layout > 1) return fail(h, FMCW_ERR_CONFIG, "unknown intensity layout");
   const uint64_t ld = sout->ld_cols ? sout->ld_cols : sout->capacity_cols;
-  CK(launch_stft_set_max_dev(h->st, global_max_dev, h->stream), "set max");
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
   CK(launch_stft_main(h->st, h->geom, h->xc.as<float>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
-                      h->derr.as<int>(), h->stream), "stft main kernel");
+                      h->derr.as<int>(), h->stream, global_max_dev), "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
   return FMCW_OK;

@@ -53,9 +53,8 @@ cudaError_t launch_compact(const CompactParams& p, cudaStream_t st);
 struct StftPlan {
   unsigned long long L_total, nfft, ncol_total, col_begin, col_end, sample_offset, L_avail;
   int log2nfft, nb, nq, n_chunks, valid;
-  unsigned int n_hard, n_refined, task_counter;
+  unsigned int n_hard, n_refined, task_counter, ticket_r, ticket_h, pad0;
   float lb_max;                 // max_t max(S0^2, 2|S(w1)|^2) (lower bound of the global max)
-  float pad2;
   double pmax_raw;              // final global max of c_j |S|^2
   int chunk_q0[MAX_CHUNKS + 1]; // query range of each chunk (multiples of 32 except the last end)
   int chunk_p0[MAX_CHUNKS + 1]; // first bin position each chunk needs
@@ -86,19 +85,18 @@ struct ShardGeom { unsigned long long L_total, sample_offset, L_local, L_avail; 
 
 cudaError_t launch_shard_pack(const float* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, float* msg,
                               cudaStream_t st);
-cudaError_t launch_shard_layout(const float* gathered, uint32_t world, uint32_t rank, uint32_t win, float* xc,
-                                ShardGeom* geom, cudaStream_t st);
-cudaError_t launch_stft_export_max(const StftTables& t, double* dst, cudaStream_t st);
 cudaError_t launch_stft_set_max_dev(const StftTables& t, const double* src, cudaStream_t st);
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st, const ShardGeom* d_geom = nullptr);
-cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st);
+                             cudaStream_t st, const float* gathered = nullptr, uint32_t world = 0, uint32_t rank = 0,
+                             float* xc = nullptr);
+cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st,
+                            double* export_dst = nullptr);
 cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout,
-                             int* d_err, cudaStream_t st);
+                             int* d_err, cudaStream_t st, const double* gmax_dev = nullptr);
 
 // tensor-core (tcgen05) STFT main kernel, window_length = 20 (stft_tc.cu)
 size_t stft_tc_table_bytes(int nb_max);
@@ -107,7 +105,7 @@ cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float
                                    cudaStream_t st);
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const float* x, float* out, const float* tcB,
                                 const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
-                                int layout, int* d_err, cudaStream_t st);
+                                int layout, int* d_err, cudaStream_t st, const double* gmax_dev = nullptr);
 int stft_variant();            // FMCW_STFT_VARIANT: -1 (default) tensor cores, 0..4 CUDA-core variants
 
 // ---- synthetic scene generator ------------------------------------------------------------------

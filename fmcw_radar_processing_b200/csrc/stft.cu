@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          uint32_t PN, unsigned long long L_total_host,
                                                          unsigned long long sample_offset,
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
-                                                         int n_chunks_req, const ShardGeom* d_geom, int coef_rows) {
+                                                         int n_chunks_req, int coef_rows, const float* __restrict__ gathered,
+                                                         uint32_t world, uint32_t rank, float* __restrict__ xc) {
   __shared__ int s_scan[1024];
   __shared__ int s_wsum[32];
   __shared__ unsigned long long s_nfft;
@@ -34,10 +35,28 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
 
   if (tid == 0) {
     unsigned long long L = L_total_host, Lloc = L_local_host, Lav = L_avail_host;
-    if (d_geom) { L = d_geom->L_total; Lloc = d_geom->L_local; Lav = d_geom->L_avail; sample_offset = d_geom->sample_offset; }
-    else if (d_ndet) { L = *d_ndet * PN; Lloc = L; Lav = L; }
+    if (gathered) {
+      // sharded run: global length, this shard's offset and the halo (the win-1 samples that follow this shard,
+      // possibly spanning several short or empty shards) from the all-gathered shard headers
+      const uint32_t stride = 2 + (win - 1), hw = win - 1;
+      unsigned long long total = 0, soff = 0, mine = 0;
+      for (uint32_t r = 0; r < world; ++r) {
+        const unsigned long long Lr = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
+        if (r < rank) soff += Lr;
+        if (r == rank) mine = Lr;
+        total += Lr;
+      }
+      uint32_t got = 0;
+      for (uint32_t r = rank + 1; r < world && got < hw; ++r) {
+        const unsigned long long Lr = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
+        const uint32_t take = (uint32_t)(Lr < (unsigned long long)(hw - got) ? Lr : (hw - got));
+        for (uint32_t i = 0; i < take; ++i) xc[mine + got + i] = gathered[r * stride + 2 + i];
+        got += take;
+      }
+      L = total; Lloc = mine; Lav = mine + got; sample_offset = soff;
+    } else if (d_ndet) { L = *d_ndet * PN; Lloc = L; Lav = L; }
     P->L_total = L; P->sample_offset = sample_offset; P->L_avail = Lav;
-    P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0; P->task_counter = 0;
+    P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0; P->task_counter = 0; P->ticket_r = 0; P->ticket_h = 0;
     int ok = (L >= (unsigned long long)win) ? 1 : 0;
     int lg = (L <= 1) ? 0 : 64 - __clzll((long long)(L - 1));
     unsigned long long nfft = 1ull << lg;
@@ -218,12 +237,22 @@ __global__ void __launch_bounds__(256) stft_colstat_kernel(StftTables t, StftGeo
   }
 }
 
+// last step of the max search: the lower bound from stft_colstat_kernel and the exhaustive results
+__device__ __forceinline__ void finalize_max(StftPlan* P, double* export_dst) {
+  const double hard = __longlong_as_double((long long)atomicMax(reinterpret_cast<unsigned long long*>(&P->pmax_raw), 0ull));
+  const double lb = (double)P->lb_max;
+  const double v = lb > hard ? lb : hard;
+  P->pmax_raw = v;
+  P->task_counter = 0;
+  if (export_dst) *export_dst = v;
+}
+
 // Columns whose trivial bound 2*(sum|y|)^2 exceeds the lower bound get a certificate: for y >= 0 the
 // spectrum is non-increasing on [0, pi/(win-1)], and on [pi/(win-1), pi] a uniform grid plus the
 // Lipschitz constant sum|n-c||y_n| bounds it.  Columns that fail go to the exhaustive list.
-__global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom g, const float* __restrict__ x) {
+__global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom g, const float* __restrict__ x, double* export_dst) {
   StftPlan* P = t.plan;
-  if (P->valid <= 0) return;
+  if (P->valid <= 0) { if (blockIdx.x == 0 && threadIdx.x == 0 && export_dst) *export_dst = 0.0; return; }
   __shared__ float s_w[1024];
   const int win = (int)g.win;
   for (int i = threadIdx.x; i < win; i += blockDim.x) s_w[i] = t.win[i];
@@ -291,6 +320,15 @@ __global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom
       }
     }
   }
+  // the last CTA to finish closes the search when no column needs the exhaustive scan
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&P->ticket_r, 1u) == gridDim.x - 1) {
+      __threadfence();
+      if (atomicAdd(&P->n_hard, 0u) == 0u) finalize_max(P, export_dst);
+    }
+  }
 }
 
 __device__ __forceinline__ void atomic_max_double_nonneg(double* addr, double v) {
@@ -298,7 +336,7 @@ __device__ __forceinline__ void atomic_max_double_nonneg(double* addr, double v)
 }
 
 // Exhaustive scan of the fine grid for the (rare) columns that have no certificate; float64.
-__global__ void __launch_bounds__(256) stft_hard_kernel(StftTables t, StftGeom g, const float* __restrict__ x) {
+__global__ void __launch_bounds__(256) stft_hard_kernel(StftTables t, StftGeom g, const float* __restrict__ x, double* export_dst) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) return;
   const unsigned nh = P->n_hard < t.hard_cap ? P->n_hard : t.hard_cap;
@@ -335,15 +373,9 @@ __global__ void __launch_bounds__(256) stft_hard_kernel(StftTables t, StftGeom g
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) best = s_red[w] > best ? s_red[w] : best;
     if (best > 0.0) atomic_max_double_nonneg(&P->pmax_raw, best);
+    __threadfence();
+    if (atomicAdd(&P->ticket_h, 1u) == gridDim.x - 1) { __threadfence(); finalize_max(P, export_dst); }
   }
-}
-
-__global__ void stft_finalize_max_kernel(StftTables t) {
-  StftPlan* P = t.plan;
-  if (P->valid <= 0) return;
-  const double lb = (double)P->lb_max;
-  if (lb > P->pmax_raw) P->pmax_raw = lb;
-  P->task_counter = 0;
 }
 
 __global__ void stft_set_max_kernel(StftTables t, double v) { t.plan->pmax_raw = v; t.plan->task_counter = 0; }
@@ -588,44 +620,11 @@ __global__ void shard_pack_kernel(const float* __restrict__ xc, const unsigned l
   if (i < win - 1) msg[2 + i] = (i < L) ? xc[i] : 0.f;
 }
 
-// from the gathered headers: global length, this shard's offset, and the halo (the win-1 samples that
-// follow this shard, possibly spanning several short or empty shards) appended to the local signal
-__global__ void shard_layout_kernel(const float* __restrict__ gathered, uint32_t world, uint32_t rank, uint32_t win,
-                                    float* __restrict__ xc, ShardGeom* __restrict__ geom) {
-  if (threadIdx.x != 0) return;
-  const uint32_t stride = 2 + (win - 1), hw = win - 1;
-  unsigned long long total = 0, off = 0, mine = 0;
-  for (uint32_t r = 0; r < world; ++r) {
-    const unsigned long long L = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
-    if (r < rank) off += L;
-    if (r == rank) mine = L;
-    total += L;
-  }
-  uint32_t got = 0;
-  for (uint32_t r = rank + 1; r < world && got < hw; ++r) {
-    const unsigned long long L = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
-    const uint32_t take = (uint32_t)(L < (unsigned long long)(hw - got) ? L : (hw - got));
-    for (uint32_t i = 0; i < take; ++i) xc[mine + got + i] = gathered[r * stride + 2 + i];
-    got += take;
-  }
-  geom->L_total = total; geom->sample_offset = off; geom->L_local = mine; geom->L_avail = mine + got;
-}
-
-__global__ void stft_export_max_kernel(StftTables t, double* dst) { *dst = (t.plan->valid > 0) ? t.plan->pmax_raw : 0.0; }
 __global__ void stft_set_max_dev_kernel(StftTables t, const double* src) { t.plan->pmax_raw = *src; t.plan->task_counter = 0; }
 
 cudaError_t launch_shard_pack(const float* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, float* msg,
                               cudaStream_t st) {
   shard_pack_kernel<<<1, 1024, 0, st>>>(xc, d_ndet, PN, win, msg);
-  return cudaGetLastError();
-}
-cudaError_t launch_shard_layout(const float* gathered, uint32_t world, uint32_t rank, uint32_t win, float* xc,
-                                ShardGeom* geom, cudaStream_t st) {
-  shard_layout_kernel<<<1, 32, 0, st>>>(gathered, world, rank, win, xc, geom);
-  return cudaGetLastError();
-}
-cudaError_t launch_stft_export_max(const StftTables& t, double* dst, cudaStream_t st) {
-  stft_export_max_kernel<<<1, 1, 0, st>>>(t, dst);
   return cudaGetLastError();
 }
 cudaError_t launch_stft_set_max_dev(const StftTables& t, const double* src, cudaStream_t st) {
@@ -651,20 +650,19 @@ int stft_variant() {
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st, const ShardGeom* d_geom) {
+                             cudaStream_t st, const float* gathered, uint32_t world, uint32_t rank, float* xc) {
   const bool tc = (g.win == 20 && stft_variant() < 0);
-  stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks, d_geom,
-                                       tc ? 2 : 0);
+  stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks,
+                                       tc ? 2 : 0, gathered, world, rank, xc);
   if (tc) return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st);
   return cudaGetLastError();
 }
 
-cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st) {
+cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st, double* export_dst) {
   const int grid = sm_count() * 8;
   stft_colstat_kernel<<<grid, 256, 0, st>>>(t, g, x);
-  stft_refine_kernel<<<grid, 256, 0, st>>>(t, g, x);
-  stft_hard_kernel<<<sm_count() * 4, 256, 0, st>>>(t, g, x);
-  stft_finalize_max_kernel<<<1, 1, 0, st>>>(t);
+  stft_refine_kernel<<<grid, 256, 0, st>>>(t, g, x, export_dst);
+  stft_hard_kernel<<<sm_count() * 4, 256, 0, st>>>(t, g, x, export_dst);
   return cudaGetLastError();
 }
 
@@ -694,10 +692,14 @@ static cudaError_t launch_main_variant(const StftTables& t, const StftGeom& g, c
 
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
-                             cudaStream_t st) {
+                             cudaStream_t st, const double* gmax_dev) {
   const int sms = sm_count();
   if (g.win == 20 && stft_variant() < 0)
-    return launch_stft_tc_main(t, g, x, out, t.tcB, t.tc_meta, capacity_cols, ld_cols, layout, d_err, st);
+    return launch_stft_tc_main(t, g, x, out, t.tcB, t.tc_meta, capacity_cols, ld_cols, layout, d_err, st, gmax_dev);
+  if (gmax_dev) {
+    cudaError_t e0 = launch_stft_set_max_dev(t, gmax_dev, st);
+    if (e0 != cudaSuccess) return e0;
+  }
   if (g.win == 20) {
     const int variant = stft_variant();
     switch (variant) {

@@ -202,7 +202,7 @@ template <int LAYOUT, int NQC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
                const uint32_t* __restrict__ tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err,
-               int dbg_mode) {
+               int dbg_mode, const double* __restrict__ gmax_dev) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
   extern __shared__ __align__(128) unsigned char smem[];
@@ -223,6 +223,9 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
   const int nq = P->nq, nb = P->nb;
   const int n_chunks = (nb - 1 + TC_STEP - 1) / TC_STEP;
   const unsigned long long n_tiles = (ncl + TC_M - 1) / TC_M;
+  // normalisation max(P): the plan's own search, or the all-reduced value of a sharded run
+  const double pmax = gmax_dev ? *gmax_dev : P->pmax_raw;
+  if (gmax_dev && blockIdx.x == 0 && threadIdx.x == 0) P->pmax_raw = pmax;
 
   // barriers: [0,1] a_full, [2,3] a_empty, [4,5] b_full, [6,7] b_empty, [8,9] t_full, [10,11] t_empty
   const uint32_t bar0 = smem_u32(&s_bar[0]);
@@ -244,7 +247,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
     const int p = tid * TC_STEP;
     s_qrng[tid] = t.qend[p < nb ? p : nb];
   }
-  if (tid < 2 * TC_HALF) s_ws[tid] = (float)((double)t.win[tid] / sqrt(P->pmax_raw));
+  if (tid < 2 * TC_HALF) s_ws[tid] = (float)((double)t.win[tid] / sqrt(pmax));
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
@@ -257,7 +260,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
     const uint32_t a_aq = smem_u32(s_aq), a_qpos = smem_u32(s_qpos);
     const uint32_t a_db = smem_u32(s_db) + (uint32_t)(qd * 32 * TC_DBS * 4);      // dB rows of this quarter's 32 columns
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const float inv = (float)(1.0 / sqrt(P->pmax_raw));
+    const float inv = (float)(1.0 / sqrt(pmax));
     // the only positions without the one-sided doubling: bin 0 (if planned) and the Nyquist bin
     const int sp0 = (t.bins[0] == 0) ? 0 : -1;
     const int sp1 = ((unsigned long long)t.bins[nb - 1] == P->nfft / 2) ? nb - 1 : -1;
@@ -479,7 +482,7 @@ cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float
 
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const float* x, float* out, const float* tcB,
                                 const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
-                                int layout, int* d_err, cudaStream_t st) {
+                                int layout, int* d_err, cudaStream_t st, const double* gmax_dev) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const size_t smem = TC_SMEM_BAR_OFF + 16 * 8 + 16;
@@ -490,7 +493,7 @@ cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const fl
   do {                                                                                                             \
     e = cudaFuncSetAttribute(stft_tc_kernel<L, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     if (e != cudaSuccess) return e;                                                                                \
-    stft_tc_kernel<L, Q><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg); \
+    stft_tc_kernel<L, Q><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg, gmax_dev); \
   } while (0)
   if (layout == 0) {
     if (g.nq == 1024) FMCW_TC_LAUNCH(0, 1024);
