@@ -237,27 +237,57 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
     }
 
     // ================= pass 2: slow-time row at the selected bin (single-bin DFT) =================
-    for (uint32_t c = warp; c < PN; c += CHAIN_WARPS) {
-      const uint32_t* cb = fbase + (uint64_t)c * NTS;
-      const int2 cs = s_csum[c];
-      float ar = 0.f, ai = 0.f;
-      for (uint32_t n = lane; n < p.nts_fft; n += 32) {
-        const uint32_t w = __ldg(cb + n);
-        const float4 wt = s_win[n];
-        const float dI = (float)((int)NTS * (int)(short)(w & 0xffffu) - cs.x);
-        const float dQ = (float)((int)NTS * ((int)w >> 16) - cs.y);
-        const float xr = fmaf(wt.x, dI, -wt.y), xi = fmaf(wt.x, dQ, -wt.z);
-        const uint32_t k = (n * (uint32_t)kbin) & (NR - 1);
+    // X_c[k*] = sum_n (gw[n]*d_c[n] - h[n]) W^(n k*) = sum_n G[n]*d_c[n] - H with G[n] = gw[n] W^(n k*) tabulated once
+    // per frame; d_c[n] = NTS*code - sum is the exact integer of pass 1.
+    float2* s_G = xch;                       // the transpose slices are free again
+    {
+      float hr = 0.f, hi = 0.f;
+      if (tid < (int)p.nts_fft) {
+        const float4 wt = s_win[tid];
+        const uint32_t k = ((uint32_t)tid * (uint32_t)kbin) & (NR - 1);
         const float tr = s_twre[k + (k >> 4)], ti = s_twim[k + (k >> 4)];
-        ar = fmaf(xr, tr, fmaf(-xi, ti, ar));
-        ai = fmaf(xr, ti, fmaf(xi, tr, ai));
+        s_G[tid] = make_float2(wt.x * tr, wt.x * ti);
+        hr = fmaf(wt.y, tr, -wt.z * ti);
+        hi = fmaf(wt.y, ti, wt.z * tr);
       }
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
-        ar += __shfl_xor_sync(0xffffffffu, ar, m);
-        ai += __shfl_xor_sync(0xffffffffu, ai, m);
+        hr += __shfl_xor_sync(0xffffffffu, hr, m);
+        hi += __shfl_xor_sync(0xffffffffu, hi, m);
       }
-      if (lane == 0) s_row[c] = make_float2(ar, ai);
+      float2* s_h = reinterpret_cast<float2*>(s_red);
+      if (lane == 0) s_h[warp] = make_float2(hr, hi);
+    }
+    __syncthreads();
+    {
+      float2* s_h = reinterpret_cast<float2*>(s_red);
+      float Hr = 0.f, Hi = 0.f;
+#pragma unroll
+      for (int w = 0; w < CHAIN_WARPS; ++w) { Hr += s_h[w].x; Hi += s_h[w].y; }
+      // eight lanes per chirp, four chirps per warp
+      const int grp = lane >> 3, j8 = lane & 7;
+      for (uint32_t c0 = warp * 4; c0 < PN; c0 += CHAIN_WARPS * 4) {
+        const uint32_t c = c0 + grp;
+        const bool live = c < PN;
+        const uint32_t* cb = fbase + (uint64_t)(live ? c : 0) * NTS;
+        const int2 cs = live ? s_csum[c] : make_int2(0, 0);
+        float ar = 0.f, ai = 0.f;
+#pragma unroll 4
+        for (uint32_t n = j8; n < p.nts_fft; n += 8) {
+          const uint32_t w = __ldg(cb + n);
+          const float2 G = s_G[n];
+          const float dI = (float)((int)NTS * (int)(short)(w & 0xffffu) - cs.x);
+          const float dQ = (float)((int)NTS * ((int)w >> 16) - cs.y);
+          ar = fmaf(G.x, dI, fmaf(-G.y, dQ, ar));
+          ai = fmaf(G.x, dQ, fmaf(G.y, dI, ai));
+        }
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1) {
+          ar += __shfl_xor_sync(0xffffffffu, ar, m);
+          ai += __shfl_xor_sync(0xffffffffu, ai, m);
+        }
+        if (live && j8 == 0) s_row[c] = make_float2(ar - Hr, ai - Hi);
+      }
     }
     __syncthreads();
 
