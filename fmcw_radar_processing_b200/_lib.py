@@ -60,6 +60,7 @@ EXPORTS = {
     "fmcw_get_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4)]),
     "fmcw_process_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(fmcw_frame_out)]),
     "fmcw_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(fmcw_frame_out), C.POINTER(fmcw_stft_out)]),
+    "fmcw_stft_frames": (C.c_int, [C.c_void_p, C.POINTER(fmcw_stft_out)]),
     "fmcw_stft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(fmcw_stft_out)]),
     "fmcw_get_slow_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "fmcw_set_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),

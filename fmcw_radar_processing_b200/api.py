@@ -148,6 +148,16 @@ class FmcwCuda:
         self._check(self.lib.fmcw_run(self._h, _ptr(iq), n, C.byref(fo), C.byref(so)))
         return out, intensity
 
+    def stft_frames(self, n_frames: int, intensity=None, layout: int = _lib.LAYOUT_TIME_MAJOR):
+        """RP:270-299 / RP:538-566 on the slow-time signal of the last ``process_frames`` call (float64 inside)."""
+        if intensity is None:
+            cols = max(1, self.max_cols(n_frames))
+            shape = (cols, self.nq) if layout == _lib.LAYOUT_TIME_MAJOR else (self.nq, cols)
+            intensity = np.empty(shape, dtype=np.float32)
+        so = self._stft_struct(intensity, layout)
+        self._check(self.lib.fmcw_stft_frames(self._h, C.byref(so)))
+        return intensity
+
     def stft(self, x, intensity=None, layout: int = _lib.LAYOUT_TIME_MAJOR):
         """RP:270-299 on an arbitrary non-negative float32 sequence."""
         L = int(x.shape[0])

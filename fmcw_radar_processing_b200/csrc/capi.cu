@@ -128,7 +128,7 @@ struct fmcw_handle {
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   std::string err;
   // chain tables
-  DevBuf win_tab, tw_pair, tw_re, tw_im, dop_tw, dop_win;
+  DevBuf win_tab, win_tab_d, tw_d, tw_pair, tw_re, tw_im, dop_tw, dop_win;
   int bin_lo = 0, bin_hi = -1;
   // STFT tables
   StftTables st{};
@@ -136,7 +136,7 @@ struct fmcw_handle {
   DevBuf plan, bins, kcb, qpos, aq, qend, coef, swin, hard, derr;
   // scratch
   DevBuf shard_geom, tcb, tcmeta, colub;
-  DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, xc, det_list, ndet, inten, synth_tab;
+  DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, o_slow64, f32_stage, xc, det_list, ndet, inten, synth_tab;
   // state
   uint64_t n_frames = 0;
   bool frames_done = false, have_info = false, planned = false;
@@ -271,9 +271,10 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   CK(pick(out ? out->range_mag : nullptr, h->o_rmag, nf * 4, false, t), "alloc"); d.rmag = (float*)t;
   CK(pick(out ? out->doppler_bin : nullptr, h->o_dbin, nf * 4, false, t), "alloc"); d.dbin = (int32_t*)t;
   CK(pick(out ? out->doppler_row : nullptr, h->o_drow, nf * ND * 8, false, t), "alloc"); d.drow = (float2*)t;
-  CK(pick(out ? out->slow_time_mag : nullptr, h->o_slow, nf * PN * 4, true, t), "alloc"); d.slow = (float*)t;
+  CK(pick(out ? out->slow_time_mag : nullptr, h->o_slow, nf * PN * 4, false, t), "alloc"); d.slow = (float*)t;
+  CK(h->o_slow64.ensure(nf * PN * sizeof(sig_t)), "alloc slow-time rows");
   CK(h->det_list.ensure(nf * 4), "alloc det_list");
-  CK(h->xc.ensure((nf * PN + c.window_length) * 4), "alloc slow-time signal");
+  CK(h->xc.ensure((nf * PN + c.window_length) * sizeof(sig_t)), "alloc slow-time signal");
   CK(h->colub.ensure((nf * PN + c.window_length) * 4), "alloc column bounds");
   h->st.col_ub = h->colub.as<float>();
 
@@ -281,18 +282,20 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   p.iq = d_iq; p.n_frames = n_frames; p.NTS = NTS; p.PN = PN; p.n_rx = n_rx; p.rx_sel = rx_sel; p.ND = ND;
   p.nts_fft = NTS < (uint32_t)NR ? NTS : (uint32_t)NR;
   p.win_tab = h->win_tab.as<float4>(); p.tw_pair = h->tw_pair.as<float2>();
+  p.win_tab_d = h->win_tab_d.as<double>(); p.tw_d = h->tw_d.as<double2>();
   p.tw_re = h->tw_re.as<float>(); p.tw_im = h->tw_im.as<float>();
   p.dop_tw = h->dop_tw.as<float2>(); p.dop_win = h->dop_win.as<float>();
   p.bin_lo = h->bin_lo; p.bin_hi = h->bin_hi;
   p.range_thr = (float)c.range_threshold; p.dop_thr = (float)c.Doppler_threshold; p.peak_mode = (int)c.peak_mode;
   p.range_max_abs = d.rmax; p.detected = d.det; p.range_bin = d.rbin; p.range_mag = d.rmag;
-  p.doppler_bin = d.dbin; p.doppler_row = d.drow; p.slow_mag = d.slow;
+  p.doppler_bin = d.dbin; p.doppler_row = d.drow; p.slow_mag = d.slow; p.slow64 = h->o_slow64.as<sig_t>();
   p.spec_out = nullptr;
   for (bool& v : h->ev_valid) v = false;
   CK(cudaEventRecord(h->ev[0], h->stream), "event"); h->ev_valid[0] = true;
   CK(launch_frame_chain(p, h->stream), "frame chain kernel");
   CK(cudaEventRecord(h->ev[1], h->stream), "event"); h->ev_valid[1] = true;
-  CompactParams cp{d.det, n_frames, PN, d.slow, h->xc.as<float>(), h->det_list.as<uint32_t>(), h->ndet.as<unsigned long long>()};
+  CompactParams cp{d.det, n_frames, PN, h->o_slow64.as<sig_t>(), h->xc.as<sig_t>(), h->det_list.as<uint32_t>(),
+                   h->ndet.as<unsigned long long>()};
   CK(launch_compact(cp, h->stream), "compaction kernels");
   CK(cudaEventRecord(h->ev[2], h->stream), "event"); h->ev_valid[2] = true;
   h->n_frames = n_frames; h->frames_done = true; h->have_info = false; h->planned = false; h->halo = 0;
@@ -340,11 +343,11 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
                         h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks, h->stream),
        "stft plan kernel");
     h->planned = true; h->plan_L = L_total; h->plan_off = offset; h->plan_avail = L_avail;
-    if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream), "stft max kernels");
+    if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream), "stft max kernels");
   }
   if (!compute_max) CK(launch_stft_set_max(h->st, pmax_override, h->stream), "stft set max");
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
-  CK(launch_stft_main(h->st, h->geom, h->xc.as<float>(), d_out, cap, d_ld, (int)sout->layout, h->derr.as<int>(), h->stream),
+  CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), d_out, cap, d_ld, (int)sout->layout, h->derr.as<int>(), h->stream),
      "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
@@ -432,6 +435,17 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
     const std::complex<double> hh = w2 * c.IF_scale * (cal[n] - cmean);
     wt[n] = make_float4((float)(w2 * c.IF_scale / (c.adc_scale * (double)NTS)), (float)hh.real(), (float)hh.imag(), 0.f);
   }
+  std::vector<double> wtd(3 * (size_t)NR, 0.0);
+  for (uint32_t n = 0; n < nts_fft; ++n) {
+    const double w2 = 2.0 * wr[n];
+    const std::complex<double> hh = w2 * c.IF_scale * (cal[n] - cmean);
+    wtd[3 * n] = w2 * c.IF_scale / (c.adc_scale * (double)NTS); wtd[3 * n + 1] = hh.real(); wtd[3 * n + 2] = hh.imag();
+  }
+  std::vector<double2> twd(NR);
+  for (int k = 0; k < NR; ++k) {
+    const double a = -2.0 * M_PI * (double)k / NR;
+    twd[k] = make_double2(std::cos(a), std::sin(a));
+  }
   std::vector<float2> twp(256);
   for (int k1 = 0; k1 < 16; ++k1)
     for (int s = 0; s < 16; ++s) {
@@ -468,6 +482,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   ok(upload(h->win_tab, wt, h->stream)); ok(upload(h->tw_pair, twp, h->stream));
+  ok(upload(h->win_tab_d, wtd, h->stream)); ok(upload(h->tw_d, twd, h->stream));
   ok(upload(h->tw_re, twre, h->stream)); ok(upload(h->tw_im, twim, h->stream));
   ok(upload(h->dop_tw, dtw, h->stream)); ok(upload(h->dop_win, dwin, h->stream));
   ok(upload(h->swin, swin, h->stream));
@@ -497,7 +512,7 @@ void fmcw_destroy(fmcw_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
-                   &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->xc, &h->det_list, &h->ndet, &h->inten,
+                   &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
                    &h->synth_tab, &h->shard_geom, &h->tcb, &h->tcmeta, &h->colub};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
@@ -589,23 +604,46 @@ fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const
   return FMCW_OK;
 }
 
+fmcw_status fmcw_stft_frames(fmcw_handle* h, const fmcw_stft_out* sout) {
+  if (!h) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  h->planned = false; h->halo = 0;
+  const uint64_t L_up = h->n_frames * h->cfg.num_chirps_per_frame;
+  const uint64_t cols_up = L_up >= h->cfg.window_length ? (L_up - h->cfg.overlap) / h->geom.hop : 0;
+  fmcw_status s = run_stft(h, true, 0, 0, 0, 0, true, 0.0, sout, cols_up);
+  if (s != FMCW_OK) return s;
+  if (sout && sout->intensity && !is_device_ptr(sout->intensity)) {
+    if (!h->have_info) { s = read_info(h); if (s != FMCW_OK) return s; }
+    if (h->plan_host.valid == 0) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length slow-time samples");
+  }
+  return FMCW_OK;
+}
+
 fmcw_status fmcw_stft(fmcw_handle* h, const float* x, uint64_t L, const fmcw_stft_out* sout) {
   if (!h || !x) return FMCW_ERR_POINTER;
   BusyGuard g(h);
   if (!g.ok) return FMCW_ERR_BUSY;
   cudaSetDevice(h->device);
   if (L < h->cfg.window_length) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length samples");
-  CK(h->xc.ensure((L + h->cfg.window_length) * 4), "alloc signal");
+  CK(h->xc.ensure((L + h->cfg.window_length) * sizeof(sig_t)), "alloc signal");
   CK(h->colub.ensure((L + h->cfg.window_length) * 4), "alloc column bounds");
   h->st.col_ub = h->colub.as<float>();
-  CK(cudaMemcpyAsync(h->xc.p, x, L * 4, is_device_ptr(x) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream),
-     "copy signal");
+  const float* d_x = x;
+  if (!is_device_ptr(x)) {
+    CK(h->f32_stage.ensure(L * 4), "alloc signal staging");
+    CK(cudaMemcpyAsync(h->f32_stage.p, x, L * 4, cudaMemcpyHostToDevice, h->stream), "copy signal");
+    d_x = h->f32_stage.as<float>();
+  }
+  CK(launch_f32_to_sig(d_x, h->xc.as<sig_t>(), L, h->stream), "widen signal");
   h->frames_done = false; h->planned = false; h->halo = 0; h->n_frames = 0;
   const uint64_t cols = (L - h->cfg.overlap) / h->geom.hop;
   return run_stft(h, false, L, 0, L, L, true, 0.0, sout, cols);
 }
 
-fmcw_status fmcw_get_slow_time(fmcw_handle* h, float* dst, uint64_t first, uint64_t count) {
+fmcw_status fmcw_get_slow_time(fmcw_handle* h, double* dst, uint64_t first, uint64_t count) {
   if (!h || (!dst && count)) return FMCW_ERR_POINTER;
   BusyGuard g(h);
   if (!g.ok) return FMCW_ERR_BUSY;
@@ -616,13 +654,13 @@ fmcw_status fmcw_get_slow_time(fmcw_handle* h, float* dst, uint64_t first, uint6
   if (first + count > L) return fail(h, FMCW_ERR_SIZE, "slow-time range out of bounds");
   if (!count) return FMCW_OK;
   const bool dev = is_device_ptr(dst);
-  CK(cudaMemcpyAsync(dst, h->xc.as<float>() + first, count * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream),
+  CK(cudaMemcpyAsync(dst, h->xc.as<sig_t>() + first, count * sizeof(sig_t), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream),
      "copy slow-time samples");
   CK(cudaStreamSynchronize(h->stream), "synchronize");
   return FMCW_OK;
 }
 
-fmcw_status fmcw_set_halo(fmcw_handle* h, const float* src, uint64_t count) {
+fmcw_status fmcw_set_halo(fmcw_handle* h, const double* src, uint64_t count) {
   if (!h || (!src && count)) return FMCW_ERR_POINTER;
   BusyGuard g(h);
   if (!g.ok) return FMCW_ERR_BUSY;
@@ -632,7 +670,7 @@ fmcw_status fmcw_set_halo(fmcw_handle* h, const float* src, uint64_t count) {
   if (!h->have_info) { fmcw_status s = read_info(h); if (s != FMCW_OK) return s; }
   const uint64_t L = h->n_det_host * h->cfg.num_chirps_per_frame;
   if (count)
-    CK(cudaMemcpyAsync(h->xc.as<float>() + L, src, count * 4,
+    CK(cudaMemcpyAsync(h->xc.as<sig_t>() + L, src, count * sizeof(sig_t),
                        is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream), "copy halo");
   h->halo = count; h->planned = false;
   return FMCW_OK;
@@ -651,7 +689,7 @@ fmcw_status fmcw_stft_local_max(fmcw_handle* h, uint64_t L_total, uint64_t sampl
   CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, L_total, sample_offset, L, L + h->halo,
                       h->n_chunks, h->stream), "stft plan kernel");
   h->planned = true; h->plan_L = L_total; h->plan_off = sample_offset; h->plan_avail = L + h->halo;
-  CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream), "stft max kernels");
+  CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream), "stft max kernels");
   fmcw_status s = read_info(h);
   if (s != FMCW_OK) return s;
   *pmax_raw_local = h->plan_host.pmax_raw;
@@ -674,19 +712,19 @@ fmcw_status fmcw_stft_sharded(fmcw_handle* h, uint64_t L_total, uint64_t sample_
 }
 
 // ---- asynchronous sharded path: every hand-off stays on the device --------------------------------
-fmcw_status fmcw_shard_pack(fmcw_handle* h, float* msg_dev) {
+fmcw_status fmcw_shard_pack(fmcw_handle* h, double* msg_dev) {
   if (!h || !msg_dev) return FMCW_ERR_POINTER;
   BusyGuard g(h);
   if (!g.ok) return FMCW_ERR_BUSY;
   cudaSetDevice(h->device);
   if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
   if (!is_device_ptr(msg_dev)) return fail(h, FMCW_ERR_POINTER, "msg must be device memory");
-  CK(launch_shard_pack(h->xc.as<float>(), h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame,
+  CK(launch_shard_pack(h->xc.as<sig_t>(), h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame,
                        h->cfg.window_length, msg_dev, h->stream), "shard pack kernel");
   return FMCW_OK;
 }
 
-fmcw_status fmcw_shard_plan(fmcw_handle* h, const float* gathered_dev, uint32_t world, uint32_t rank, double* local_max_dev) {
+fmcw_status fmcw_shard_plan(fmcw_handle* h, const double* gathered_dev, uint32_t world, uint32_t rank, double* local_max_dev) {
   if (!h || !gathered_dev || !local_max_dev) return FMCW_ERR_POINTER;
   BusyGuard g(h);
   if (!g.ok) return FMCW_ERR_BUSY;
@@ -695,8 +733,8 @@ fmcw_status fmcw_shard_plan(fmcw_handle* h, const float* gathered_dev, uint32_t 
   if (rank >= world) return fail(h, FMCW_ERR_SIZE, "rank >= world");
   if (!is_device_ptr(gathered_dev) || !is_device_ptr(local_max_dev)) return fail(h, FMCW_ERR_POINTER, "device memory required");
   CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
-                      gathered_dev, world, rank, h->xc.as<float>()), "stft plan kernel");
-  CK(launch_stft_max(h->st, h->geom, h->xc.as<float>(), h->stream, local_max_dev), "stft max kernels");
+                      gathered_dev, world, rank, h->xc.as<sig_t>()), "stft plan kernel");
+  CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream, local_max_dev), "stft max kernels");
   h->planned = true; h->have_info = false;
   return FMCW_OK;
 }
@@ -711,7 +749,7 @@ fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const 
   if (sout->layout > 1) return fail(h, FMCW_ERR_CONFIG, "unknown intensity layout");
   const uint64_t ld = sout->ld_cols ? sout->ld_cols : sout->capacity_cols;
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
-  CK(launch_stft_main(h->st, h->geom, h->xc.as<float>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
+  CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
                       h->derr.as<int>(), h->stream, global_max_dev), "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
@@ -766,8 +804,11 @@ fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_fr
   p.n_rx = c.num_Rx_antennas; p.rx_sel = c.rx_select; p.ND = c.Doppler_fft_size;
   p.nts_fft = p.NTS < (uint32_t)NR ? p.NTS : (uint32_t)NR;
   p.win_tab = h->win_tab.as<float4>(); p.tw_pair = h->tw_pair.as<float2>();
+  p.win_tab_d = h->win_tab_d.as<double>(); p.tw_d = h->tw_d.as<double2>();
   p.tw_re = h->tw_re.as<float>(); p.tw_im = h->tw_im.as<float>();
   p.dop_tw = h->dop_tw.as<float2>(); p.dop_win = h->dop_win.as<float>();
+  CK(h->o_slow64.ensure((size_t)c.num_chirps_per_frame * sizeof(sig_t)), "alloc");
+  p.slow64 = h->o_slow64.as<sig_t>();
   p.bin_lo = NR; p.bin_hi = -1;   // no detection work
   p.range_thr = 0.f; p.dop_thr = 0.f; p.peak_mode = 0;
   const bool dev = is_device_ptr(out);

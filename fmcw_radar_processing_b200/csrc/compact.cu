@@ -41,10 +41,10 @@ __global__ void __launch_bounds__(1024) scan_flags_kernel(const int32_t* __restr
   if (tid == 0) *n_det = s_carry;
 }
 
-__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ slow_mag,
+__global__ void __launch_bounds__(256) gather_rows_kernel(const sig_t* __restrict__ slow_mag,
                                                           const uint32_t* __restrict__ det_list,
                                                           const unsigned long long* __restrict__ n_det, uint32_t PN,
-                                                          uint64_t n_frames, float* __restrict__ xc) {
+                                                          uint64_t n_frames, sig_t* __restrict__ xc) {
   const unsigned long long L = *n_det * PN;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < L;
        i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -61,6 +61,20 @@ cudaError_t launch_compact(const CompactParams& p, cudaStream_t st) {
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks == 0) blocks = 1;
   gather_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.slow_mag, p.det_list, p.n_det, p.PN, p.n_frames, p.xc);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) f32_to_sig_kernel(const float* __restrict__ src, sig_t* __restrict__ dst, unsigned long long n) {
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    dst[i] = (sig_t)src[i];
+}
+
+cudaError_t launch_f32_to_sig(const float* src, sig_t* dst, unsigned long long n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  unsigned long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_sig_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n);
   return cudaGetLastError();
 }
 

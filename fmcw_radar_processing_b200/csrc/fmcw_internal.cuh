@@ -5,6 +5,8 @@
 
 namespace fmcw {
 
+typedef double sig_t;           // slow-time magnitude signal: float64 from the single-bin DFT to the STFT operands
+
 constexpr int NR = 256;           // range_fft_size (RP:118); the radix-16 x radix-16 core is built for it
 constexpr int MAX_ND = 64;        // Doppler_fft_size upper bound
 constexpr int MAX_NQ = 1024;      // MAX_FREQ_BINS upper bound (RP:293)
@@ -21,6 +23,8 @@ struct ChainParams {
   uint32_t NTS, PN, n_rx, rx_sel, ND;
   uint32_t nts_fft;          // min(NTS, NR): samples that enter the FFT (fft(x,256,1) truncates, RP:205)
   const float4* win_tab;     // [nts_fft] {gw, h_re, h_im, 0}: xw = gw*(NTS*code - sum) - h
+  const double* win_tab_d;   // [nts_fft][3] the same table in float64 (slow-time row)
+  const double2* tw_d;       // [256] W_256^k in float64
   const float2* tw_pair;     // [16][16] W_256^(s*k1)
   const float*  tw_re;       // [272] skewed W_256^k table (index k + k/16)
   const float*  tw_im;
@@ -32,6 +36,7 @@ struct ChainParams {
   // outputs, device pointers, any may be null
   float* range_max_abs; int32_t* detected; int32_t* range_bin; float* range_mag;
   int32_t* doppler_bin; float2* doppler_row; float* slow_mag;
+  sig_t* slow64;             // [n_frames][PN] float64 magnitudes (always written; feeds the compaction)
   // optional: range spectrum of one (frame, chirp) (RP:410-411)
   float* spec_out; uint64_t spec_frame; uint32_t spec_chirp;
 };
@@ -42,8 +47,8 @@ cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st);
 // ---- compaction of the detected frames' slow-time rows (RP:257-260) ------------------------------
 struct CompactParams {
   const int32_t* detected; uint64_t n_frames; uint32_t PN;
-  const float* slow_mag;      // [n_frames][PN]
-  float* xc;                  // compacted magnitudes
+  const sig_t* slow_mag;      // [n_frames][PN]
+  sig_t* xc;                  // compacted magnitudes
   uint32_t* det_list;         // [n_frames] frame index of the k-th detection
   unsigned long long* n_det;  // device scalar
 };
@@ -83,18 +88,18 @@ struct StftGeom { uint32_t win, hop, nq; double fs; };
 struct ShardGeom { unsigned long long L_total, sample_offset, L_local, L_avail; };
 
 
-cudaError_t launch_shard_pack(const float* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, float* msg,
+cudaError_t launch_shard_pack(const sig_t* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, double* msg,
                               cudaStream_t st);
 cudaError_t launch_stft_set_max_dev(const StftTables& t, const double* src, cudaStream_t st);
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st, const float* gathered = nullptr, uint32_t world = 0, uint32_t rank = 0,
-                             float* xc = nullptr);
-cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st,
+                             cudaStream_t st, const double* gathered = nullptr, uint32_t world = 0, uint32_t rank = 0,
+                             sig_t* xc = nullptr);
+cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const sig_t* x, cudaStream_t st,
                             double* export_dst = nullptr);
 cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
-cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
+cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout,
                              int* d_err, cudaStream_t st, const double* gmax_dev = nullptr);
 
@@ -103,10 +108,12 @@ size_t stft_tc_table_bytes(int nb_max);
 size_t stft_tc_meta_bytes(int nb_max);
 cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t* tc_meta, int nb_max,
                                    cudaStream_t st);
-cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const float* x, float* out, const float* tcB,
+cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
                                 const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev = nullptr);
 int stft_variant();            // FMCW_STFT_VARIANT: -1 (default) tensor cores, 0..4 CUDA-core variants
+
+cudaError_t launch_f32_to_sig(const float* src, sig_t* dst, unsigned long long n, cudaStream_t st);
 
 // ---- synthetic scene generator ------------------------------------------------------------------
 cudaError_t launch_synth(const double* tables, uint32_t n_scat, uint64_t seed, uint64_t frame0, uint64_t n_frames,

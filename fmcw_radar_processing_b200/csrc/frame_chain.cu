@@ -230,38 +230,37 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
       if (p.range_mag) p.range_mag[f] = det ? s_rmax[kbin] : 0.f;
     }
     if (!det) {
-      if (p.slow_mag) for (uint32_t c = tid; c < PN; c += CHAIN_THREADS) p.slow_mag[f * PN + c] = 0.f;
+      for (uint32_t c = tid; c < PN; c += CHAIN_THREADS) { p.slow64[f * PN + c] = 0.0; if (p.slow_mag) p.slow_mag[f * PN + c] = 0.f; }
       if (p.doppler_row && tid < (int)ND) p.doppler_row[f * ND + tid] = make_float2(0.f, 0.f);
       if (p.doppler_bin && tid == 0) p.doppler_bin[f] = (int)ND / 2;
       continue;
     }
 
-    // ================= pass 2: slow-time row at the selected bin (single-bin DFT) =================
+    // ================= pass 2: slow-time row at the selected bin (single-bin DFT, float64) =================
     // X_c[k*] = sum_n (gw[n]*d_c[n] - h[n]) W^(n k*) = sum_n G[n]*d_c[n] - H with G[n] = gw[n] W^(n k*) tabulated once
-    // per frame; d_c[n] = NTS*code - sum is the exact integer of pass 1.
-    float2* s_G = xch;                       // the transpose slices are free again
+    // per frame; d_c[n] = NTS*code - sum is the exact integer of pass 1.  This row feeds the STFT, whose bins sit
+    // 100+ dB under its DC term, so it is carried in float64 (8,192 complex MACs per frame).
+    double2* s_G = reinterpret_cast<double2*>(xch);          // the transpose slices are free again
+    double2* s_h = reinterpret_cast<double2*>(xch) + NR;     // [CHAIN_WARPS]
     {
-      float hr = 0.f, hi = 0.f;
+      double hr = 0.0, hi = 0.0;
       if (tid < (int)p.nts_fft) {
-        const float4 wt = s_win[tid];
-        const uint32_t k = ((uint32_t)tid * (uint32_t)kbin) & (NR - 1);
-        const float tr = s_twre[k + (k >> 4)], ti = s_twim[k + (k >> 4)];
-        s_G[tid] = make_float2(wt.x * tr, wt.x * ti);
-        hr = fmaf(wt.y, tr, -wt.z * ti);
-        hi = fmaf(wt.y, ti, wt.z * tr);
+        const double gw = p.win_tab_d[3 * tid], h_re = p.win_tab_d[3 * tid + 1], h_im = p.win_tab_d[3 * tid + 2];
+        const double2 tw = p.tw_d[((uint32_t)tid * (uint32_t)kbin) & (NR - 1)];
+        s_G[tid] = make_double2(gw * tw.x, gw * tw.y);
+        hr = h_re * tw.x - h_im * tw.y;
+        hi = h_re * tw.y + h_im * tw.x;
       }
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
         hr += __shfl_xor_sync(0xffffffffu, hr, m);
         hi += __shfl_xor_sync(0xffffffffu, hi, m);
       }
-      float2* s_h = reinterpret_cast<float2*>(s_red);
-      if (lane == 0) s_h[warp] = make_float2(hr, hi);
+      if (lane == 0) s_h[warp] = make_double2(hr, hi);
     }
     __syncthreads();
     {
-      float2* s_h = reinterpret_cast<float2*>(s_red);
-      float Hr = 0.f, Hi = 0.f;
+      double Hr = 0.0, Hi = 0.0;
 #pragma unroll
       for (int w = 0; w < CHAIN_WARPS; ++w) { Hr += s_h[w].x; Hi += s_h[w].y; }
       // eight lanes per chirp, four chirps per warp
@@ -271,31 +270,36 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
         const bool live = c < PN;
         const uint32_t* cb = fbase + (uint64_t)(live ? c : 0) * NTS;
         const int2 cs = live ? s_csum[c] : make_int2(0, 0);
-        float ar = 0.f, ai = 0.f;
+        double ar = 0.0, ai = 0.0;
 #pragma unroll 4
         for (uint32_t n = j8; n < p.nts_fft; n += 8) {
           const uint32_t w = __ldg(cb + n);
-          const float2 G = s_G[n];
-          const float dI = (float)((int)NTS * (int)(short)(w & 0xffffu) - cs.x);
-          const float dQ = (float)((int)NTS * ((int)w >> 16) - cs.y);
-          ar = fmaf(G.x, dI, fmaf(-G.y, dQ, ar));
-          ai = fmaf(G.x, dQ, fmaf(G.y, dI, ai));
+          const double2 G = s_G[n];
+          const double dI = (double)((int)NTS * (int)(short)(w & 0xffffu) - cs.x);
+          const double dQ = (double)((int)NTS * ((int)w >> 16) - cs.y);
+          ar = fma(G.x, dI, fma(-G.y, dQ, ar));
+          ai = fma(G.x, dQ, fma(G.y, dI, ai));
         }
 #pragma unroll
         for (int m = 4; m >= 1; m >>= 1) {
           ar += __shfl_xor_sync(0xffffffffu, ar, m);
           ai += __shfl_xor_sync(0xffffffffu, ai, m);
         }
-        if (live && j8 == 0) s_row[c] = make_float2(ar - Hr, ai - Hi);
+        if (live && j8 == 0) {
+          const double xr = ar - Hr, xi = ai - Hi;
+          s_row[c] = make_float2((float)xr, (float)xi);
+          const double mag = sqrt(xr * xr + xi * xi);          // RP:259 + RP:270
+          p.slow64[f * PN + c] = mag;
+          if (p.slow_mag) p.slow_mag[f * PN + c] = (float)mag;
+        }
       }
     }
     __syncthreads();
 
-    // slow-time magnitudes (RP:259 + RP:270) and the mean over all PN chirps (RP:217)
+    // mean over all PN chirps (RP:217)
     float sr = 0.f, si = 0.f;
     for (uint32_t c = tid; c < PN; c += CHAIN_THREADS) {
       const float2 r = s_row[c];
-      if (p.slow_mag) p.slow_mag[f * PN + c] = sqrtf(fmaf(r.x, r.x, r.y * r.y));
       sr += r.x;
       si += r.y;
     }

@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          uint32_t PN, unsigned long long L_total_host,
                                                          unsigned long long sample_offset,
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
-                                                         int n_chunks_req, int coef_rows, const float* __restrict__ gathered,
-                                                         uint32_t world, uint32_t rank, float* __restrict__ xc) {
+                                                         int n_chunks_req, int coef_rows, const double* __restrict__ gathered,
+                                                         uint32_t world, uint32_t rank, sig_t* __restrict__ xc) {
   __shared__ int s_scan[1024];
   __shared__ int s_wsum[32];
   __shared__ unsigned long long s_nfft;
@@ -38,19 +38,19 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
     if (gathered) {
       // sharded run: global length, this shard's offset and the halo (the win-1 samples that follow this shard,
       // possibly spanning several short or empty shards) from the all-gathered shard headers
-      const uint32_t stride = 2 + (win - 1), hw = win - 1;
+      const uint32_t stride = 1 + (win - 1), hw = win - 1;
       unsigned long long total = 0, soff = 0, mine = 0;
       for (uint32_t r = 0; r < world; ++r) {
-        const unsigned long long Lr = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
+        const unsigned long long Lr = (unsigned long long)gathered[r * stride];
         if (r < rank) soff += Lr;
         if (r == rank) mine = Lr;
         total += Lr;
       }
       uint32_t got = 0;
       for (uint32_t r = rank + 1; r < world && got < hw; ++r) {
-        const unsigned long long Lr = (unsigned long long)gathered[r * stride] + ((unsigned long long)gathered[r * stride + 1] << 20);
+        const unsigned long long Lr = (unsigned long long)gathered[r * stride];
         const uint32_t take = (uint32_t)(Lr < (unsigned long long)(hw - got) ? Lr : (hw - got));
-        for (uint32_t i = 0; i < take; ++i) xc[mine + got + i] = gathered[r * stride + 2 + i];
+        for (uint32_t i = 0; i < take; ++i) xc[mine + got + i] = gathered[r * stride + 1 + i];
         got += take;
       }
       L = total; Lloc = mine; Lav = mine + got; sample_offset = soff;
@@ -195,7 +195,7 @@ __device__ __forceinline__ float atomic_max_nonneg(float* addr, float v) {
 }
 
 // per column: S0 = sum y, S1 = |S(w_1)|^2; lower bound max(S0^2, c_1 |S1|^2)
-__global__ void __launch_bounds__(256) stft_colstat_kernel(StftTables t, StftGeom g, const float* __restrict__ x) {
+__global__ void __launch_bounds__(256) stft_colstat_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x) {
   const StftPlan* P = t.plan;
   if (P->valid <= 0) return;
   __shared__ float s_w[1024];
@@ -211,18 +211,18 @@ __global__ void __launch_bounds__(256) stft_colstat_kernel(StftTables t, StftGeo
   float best = 0.f;
   for (unsigned long long col = cb + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; col < ce;
        col += (unsigned long long)gridDim.x * blockDim.x) {
-    const float* xs = x + (col * g.hop - off);
+    const sig_t* xs = x + (col * g.hop - off);
     float s0 = 0.f, re = 0.f, im = 0.f, sabs = 0.f;
     const int cidx = half;   // centre tap for odd windows
     for (int m = 0; m < half; ++m) {
       const int lo = odd ? (cidx - 1 - m) : (half - 1 - m), hi = odd ? (cidx + 1 + m) : (half + m);
-      const float ylo = s_w[lo] * xs[lo], yhi = s_w[hi] * xs[hi];
+      const float ylo = s_w[lo] * (float)xs[lo], yhi = s_w[hi] * (float)xs[hi];
       s0 += ylo + yhi;
       sabs += fabsf(ylo) + fabsf(yhi);
       re = fmaf(ylo + yhi, s_c1[m], re);
       im = fmaf(ylo - yhi, s_c1[half + m], im);
     }
-    if (odd) { const float yc = s_w[cidx] * xs[cidx]; s0 += yc; re += yc; sabs += fabsf(yc); }
+    if (odd) { const float yc = s_w[cidx] * (float)xs[cidx]; s0 += yc; re += yc; sabs += fabsf(yc); }
     const float lb = fmaxf(s0 * s0, c1 * fmaf(re, re, im * im));
     best = fmaxf(best, lb);
     t.col_ub[col - cb] = 2.f * sabs * sabs;          // trivial upper bound of this column's maximum
@@ -250,7 +250,7 @@ __device__ __forceinline__ void finalize_max(StftPlan* P, double* export_dst) {
 // Columns whose trivial bound 2*(sum|y|)^2 exceeds the lower bound get a certificate: for y >= 0 the
 // spectrum is non-increasing on [0, pi/(win-1)], and on [pi/(win-1), pi] a uniform grid plus the
 // Lipschitz constant sum|n-c||y_n| bounds it.  Columns that fail go to the exhaustive list.
-__global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom g, const float* __restrict__ x, double* export_dst) {
+__global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, double* export_dst) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (blockIdx.x == 0 && threadIdx.x == 0 && export_dst) *export_dst = 0.0; return; }
   __shared__ float s_w[1024];
@@ -268,10 +268,10 @@ __global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom
     bool cand = false, nonneg = true;
     float dl = 0.f;
     if (col < ce && t.col_ub[col - cb] > lb) {         // only columns whose trivial bound beats the lower bound
-      const float* xs = x + (col * g.hop - off);
+      const sig_t* xs = x + (col * g.hop - off);
       const float c0 = 0.5f * (float)(win - 1);
       for (int n = 0; n < win; ++n) {
-        const float y = s_w[n] * xs[n];
+        const float y = s_w[n] * (float)xs[n];
         nonneg = nonneg && (y >= 0.f);
         dl = fmaf(fabsf((float)n - c0), fabsf(y), dl);
       }
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom
       const float c_dl = __shfl_sync(0xffffffffu, dl, src);
       bool fail = !c_nonneg;
       if (!fail && win > 2) {
-        const float* xs = x + (ccol * g.hop - off);
+        const sig_t* xs = x + (ccol * g.hop - off);
         const float w_lo = 3.14159265358979f / (float)(win - 1);
         const int G = 32 * win;
         const float delta = (3.14159265358979f - w_lo) / (float)G;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom
           float ar = 0.f, ai = 0.f;
           for (int n = win - 1; n >= 0; --n) {
             const float tr = fmaf(ar, cs, ai * sn), ti = fmaf(ai, cs, -ar * sn);
-            ar = tr + s_w[n] * xs[n];
+            ar = tr + s_w[n] * (float)xs[n];
             ai = ti;
           }
           const float mag = sqrtf(fmaf(ar, ar, ai * ai)) + slack;
@@ -336,7 +336,7 @@ __device__ __forceinline__ void atomic_max_double_nonneg(double* addr, double v)
 }
 
 // Exhaustive scan of the fine grid for the (rare) columns that have no certificate; float64.
-__global__ void __launch_bounds__(256) stft_hard_kernel(StftTables t, StftGeom g, const float* __restrict__ x, double* export_dst) {
+__global__ void __launch_bounds__(256) stft_hard_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, double* export_dst) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) return;
   const unsigned nh = P->n_hard < t.hard_cap ? P->n_hard : t.hard_cap;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) stft_hard_kernel(StftTables t, StftGeom g
   double best = 0.0;
   for (unsigned h = 0; h < nh; ++h) {
     const unsigned long long col = P->col_begin + t.hard_list[h];
-    const float* xs = x + (col * g.hop - P->sample_offset);
+    const sig_t* xs = x + (col * g.hop - P->sample_offset);
     __syncthreads();
     for (int i = threadIdx.x; i < win; i += blockDim.x) s_y[i] = (double)t.win[i] * (double)xs[i];
     __syncthreads();
@@ -431,7 +431,7 @@ __device__ __forceinline__ void flush_stage(uint32_t a_stage, int ncols_valid, f
 
 template <int HALF, int CPT, int QF, int LAYOUT, int MAIN_THREADS, int MINB>
 __global__ void __launch_bounds__(MAIN_THREADS, MINB)
-stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out,
+stft_main_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __restrict__ out,
                  unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
@@ -492,10 +492,10 @@ stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* _
     for (int c = 0; c < CPT; ++c) {
       unsigned long long col = warp_col0 + c * 32 + lane;
       if (col >= ce) col = ce - 1;
-      const float* xs = x + (col * g.hop - off);
+      const sig_t* xs = x + (col * g.hop - off);
 #pragma unroll
       for (int m = 0; m < HALF; ++m) {
-        const float ylo = s_ws[HALF - 1 - m] * __ldg(xs + HALF - 1 - m), yhi = s_ws[HALF + m] * __ldg(xs + HALF + m);
+        const float ylo = s_ws[HALF - 1 - m] * (float)__ldg(xs + HALF - 1 - m), yhi = s_ws[HALF + m] * (float)__ldg(xs + HALF + m);
         e[c][m] = ylo + yhi;
         o[c][m] = ylo - yhi;
       }
@@ -561,7 +561,7 @@ stft_main_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* _
 // Correct for every configuration; the specialised kernel above is the fast path for the reference's
 // window_length = 20.
 template <int LAYOUT>
-__global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeom g, const float* __restrict__ x,
+__global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x,
                                                            float* __restrict__ out, unsigned long long capacity_cols,
                                                            unsigned long long ld_cols, int* d_err) {
   const StftPlan* P = t.plan;
@@ -579,14 +579,14 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeo
     unsigned long long col = cb + blk * 128 + tid;
     const bool act = col < ce;
     if (!act) col = ce - 1;
-    const float* xs = x + (col * g.hop - off);
+    const sig_t* xs = x + (col * g.hop - off);
     for (int m = 0; m < half; ++m) {
       const int lo = odd ? (half - 1 - m) : (half - 1 - m), hi = odd ? (half + 1 + m) : (half + m);
-      const float ylo = t.win[lo] * inv * xs[lo], yhi = t.win[hi] * inv * xs[hi];
+      const float ylo = t.win[lo] * inv * (float)xs[lo], yhi = t.win[hi] * inv * (float)xs[hi];
       s_dyn[m * 128 + tid] = ylo + yhi;
       s_dyn[(half + m) * 128 + tid] = ylo - yhi;
     }
-    const float yc = odd ? t.win[half] * inv * xs[half] : 0.f;
+    const float yc = odd ? t.win[half] * inv * (float)xs[half] : 0.f;
     float prev = 0.f;
     for (int p = 0; p < nb; ++p) {
       const float* cf = t.coef + (size_t)p * 2 * half;
@@ -611,18 +611,18 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeo
 // ------------------------------------------------------------------------------------------------
 // device-side hand-offs of the sharded path (no host round trip between the collectives)
 // ------------------------------------------------------------------------------------------------
-// msg = {L_local & 0xFFFFF, L_local >> 20, first win-1 samples}: the shard header that is all-gathered
-__global__ void shard_pack_kernel(const float* __restrict__ xc, const unsigned long long* __restrict__ d_ndet, uint32_t PN,
-                                  uint32_t win, float* __restrict__ msg) {
+// msg = {L_local, first win-1 samples} in float64: the shard header that is all-gathered
+__global__ void shard_pack_kernel(const sig_t* __restrict__ xc, const unsigned long long* __restrict__ d_ndet, uint32_t PN,
+                                  uint32_t win, double* __restrict__ msg) {
   const unsigned long long L = *d_ndet * PN;
   const uint32_t i = threadIdx.x;
-  if (i == 0) { msg[0] = (float)(L & 0xFFFFFull); msg[1] = (float)(L >> 20); }
-  if (i < win - 1) msg[2 + i] = (i < L) ? xc[i] : 0.f;
+  if (i == 0) msg[0] = (double)L;
+  if (i < win - 1) msg[1 + i] = (i < L) ? xc[i] : 0.0;
 }
 
 __global__ void stft_set_max_dev_kernel(StftTables t, const double* src) { t.plan->pmax_raw = *src; t.plan->task_counter = 0; }
 
-cudaError_t launch_shard_pack(const float* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, float* msg,
+cudaError_t launch_shard_pack(const sig_t* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, double* msg,
                               cudaStream_t st) {
   shard_pack_kernel<<<1, 1024, 0, st>>>(xc, d_ndet, PN, win, msg);
   return cudaGetLastError();
@@ -650,7 +650,7 @@ int stft_variant() {
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st, const float* gathered, uint32_t world, uint32_t rank, float* xc) {
+                             cudaStream_t st, const double* gathered, uint32_t world, uint32_t rank, sig_t* xc) {
   const bool tc = (g.win == 20 && stft_variant() < 0);
   stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks,
                                        tc ? 2 : 0, gathered, world, rank, xc);
@@ -658,7 +658,7 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
   return cudaGetLastError();
 }
 
-cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const float* x, cudaStream_t st, double* export_dst) {
+cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const sig_t* x, cudaStream_t st, double* export_dst) {
   const int grid = sm_count() * 8;
   stft_colstat_kernel<<<grid, 256, 0, st>>>(t, g, x);
   stft_refine_kernel<<<grid, 256, 0, st>>>(t, g, x, export_dst);
@@ -672,7 +672,7 @@ cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream
 }
 
 template <int HALF, int CPT, int QF, int THREADS, int MINB>
-static cudaError_t launch_main_variant(const StftTables& t, const StftGeom& g, const float* x, float* out,
+static cudaError_t launch_main_variant(const StftTables& t, const StftGeom& g, const sig_t* x, float* out,
                                        unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
                                        cudaStream_t st, int sms) {
   const size_t base = (size_t)(NP_MAX * 2 * HALF + 2 * NP_MAX + MAX_NQ + 2 * HALF + 4) * sizeof(float);
@@ -690,7 +690,7 @@ static cudaError_t launch_main_variant(const StftTables& t, const StftGeom& g, c
   return cudaGetLastError();
 }
 
-cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const float* x, float* out,
+cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
                              cudaStream_t st, const double* gmax_dev) {
   const int sms = sm_count();

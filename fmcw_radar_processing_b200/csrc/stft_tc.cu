@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
 // ------------------------------------------------------------------------------------------------
 template <int LAYOUT, int NQC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
+stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
                const uint32_t* __restrict__ tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err,
                int dbg_mode, const double* __restrict__ gmax_dev) {
   StftPlan* P = t.plan;
@@ -269,16 +269,21 @@ stft_tc_kernel(StftTables t, StftGeom g, const float* __restrict__ x, float* __r
     auto build_a = [&](unsigned long long tile, int buf) {
       unsigned long long col = cb + tile * TC_M + m;
       if (col >= ce) col = ce - 1;
-      const float* xs = x + (col * g.hop - off);
-      float xv[2 * TC_HALF];
-      float mean = 0.f;
+      const sig_t* xs = x + (col * g.hop - off);
+      // float64 samples: the mean is removed in float64, only the small residual is rounded to float32
+      double xd[2 * TC_HALF];
+      double mean_d = 0.0;
 #pragma unroll
-      for (int n = 0; n < 2 * TC_HALF; ++n) { xv[n] = __ldg(xs + n); mean += xv[n]; }
-      mean *= (1.0f / (2 * TC_HALF));
+      for (int n = 0; n < 2 * TC_HALF; ++n) { xd[n] = __ldg(xs + n); mean_d += xd[n]; }
+      mean_d *= (1.0 / (2 * TC_HALF));
+      const float mean = (float)mean_d;        // the DC tap carries the float32 mean; its rounding error joins the residual
+      float xv[2 * TC_HALF];
+#pragma unroll
+      for (int n = 0; n < 2 * TC_HALF; ++n) xv[n] = (float)(xd[n] - (double)mean);
       float v[TC_KP];
 #pragma unroll
       for (int k = 0; k < TC_HALF; ++k) {
-        const float ylo = s_ws[TC_HALF - 1 - k] * (xv[TC_HALF - 1 - k] - mean), yhi = s_ws[TC_HALF + k] * (xv[TC_HALF + k] - mean);
+        const float ylo = s_ws[TC_HALF - 1 - k] * xv[TC_HALF - 1 - k], yhi = s_ws[TC_HALF + k] * xv[TC_HALF + k];
         v[k] = (sw < 2) ? (ylo + yhi) : (ylo - yhi);
       }
       v[TC_HALF] = (sw < 2) ? mean * inv : 0.f;           // DC tap: multiplies the tabulated window response
@@ -480,7 +485,7 @@ cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float
   return cudaGetLastError();
 }
 
-cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const float* x, float* out, const float* tcB,
+cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
                                 const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev) {
   static int sms = 0;

@@ -33,22 +33,19 @@ class ShardLayout:
 
 def exchange_heads(x_local: torch.Tensor, L_local: int, window_length: int, group=None) -> ShardLayout:
     """Collective 1.  ``x_local`` holds at least ``min(L_local, window_length-1)`` leading samples of this
-    rank's slow-time magnitude signal (float32, on the backend's device)."""
+    rank's slow-time magnitude signal (float64, on the backend's device)."""
     ws, rank = dist.get_world_size(group), dist.get_rank(group)
     hw = window_length - 1
     dev = x_local.device
-    msg = torch.zeros(2 + hw, dtype=torch.float32, device=dev)
-    # the length travels as two exact float32 halves (lengths can exceed 2^24)
-    msg[0] = float(L_local & 0xFFFFF)
-    msg[1] = float(L_local >> 20)
+    msg = torch.zeros(1 + hw, dtype=torch.float64, device=dev)
+    msg[0] = float(L_local)                  # exact in float64
     n_head = min(L_local, hw)
     if n_head:
-        msg[2:2 + n_head] = x_local[:n_head]
+        msg[1:1 + n_head] = x_local[:n_head]
     gathered = [torch.empty_like(msg) for _ in range(ws)]
     dist.all_gather(gathered, msg, group=group)
     heads = torch.stack(gathered)
-    meta = heads[:, :2].to("cpu", torch.float64).numpy()
-    lengths = [int(lo) + (int(hi) << 20) for lo, hi in meta]
+    lengths = [int(v) for v in heads[:, 0].to("cpu").numpy()]
     offsets = [int(v) for v in np.concatenate([[0], np.cumsum(lengths)[:-1]])]
     # assemble the halo from the heads of the following ranks (skipping short / empty shards)
     parts, need = [], hw
@@ -57,9 +54,9 @@ def exchange_heads(x_local: torch.Tensor, L_local: int, window_length: int, grou
             break
         take = min(need, lengths[r], hw)
         if take:
-            parts.append(heads[r, 2:2 + take])
+            parts.append(heads[r, 1:1 + take])
             need -= take
-    halo = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.float32, device=dev)
+    halo = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.float64, device=dev)
     return ShardLayout(lengths, offsets, int(sum(lengths)), halo)
 
 
@@ -108,9 +105,9 @@ class ShardedRun:
     def _async_buffers(self, dev):
         if getattr(self, "_bufs", None) is None:
             ws = dist.get_world_size(self.group)
-            n = 2 + self.h.cfg["window_length"] - 1
-            self._bufs = dict(msg=torch.zeros(n, dtype=torch.float32, device=dev),
-                              gathered=torch.zeros(ws * n, dtype=torch.float32, device=dev),
+            n = 1 + self.h.cfg["window_length"] - 1
+            self._bufs = dict(msg=torch.zeros(n, dtype=torch.float64, device=dev),
+                              gathered=torch.zeros(ws * n, dtype=torch.float64, device=dev),
                               gmax=torch.zeros(1, dtype=torch.float64, device=dev),
                               lib_stream=torch.cuda.ExternalStream(self.h.stream, device=dev))
         return self._bufs
@@ -161,7 +158,7 @@ class ShardedRun:
         info = h.info()
         L_local = info["L_local"]
         win = h.cfg["window_length"]
-        head = torch.zeros(win - 1, dtype=torch.float32, device=dev)
+        head = torch.zeros(win - 1, dtype=torch.float64, device=dev)
         n_head = min(L_local, win - 1)
         if n_head:
             h.get_slow_time(head, 0, n_head)

@@ -124,8 +124,7 @@ def _branch_yes(h, cfg, frame, N, filename, workdir, result):
         if L >= cfg["window_length"]:                                # RP:534
             plot_counter += 1
             if plot_counter <= max_plots:                            # RP:537
-                x = np.ascontiguousarray(out["slow_time_mag"][det].reshape(-1))
-                inten = h.stft(x)                                    # RP:538-566
+                inten = h.stft_frames(e0 - s0 + 1)                   # RP:538-566 on the batch's own signal
                 ncol = h.info()["ncol_local"]
                 T, F, nfft, _ = h.stft_axes(L)
                 name = f"{filename}_spectrogram_batch_{batch}.json"  # RP:587

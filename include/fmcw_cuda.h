@@ -151,6 +151,10 @@ FMCW_API fmcw_status fmcw_process_frames(fmcw_handle* h, const int16_t* iq, uint
 FMCW_API fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,
                               const fmcw_frame_out* fout, const fmcw_stft_out* sout);
 
+/* STFT (RP:270-299 / RP:538-566) of the slow-time signal gathered by the last fmcw_process_frames on this handle
+ * (the float64 magnitudes of the detected frames): the second half of fmcw_run. */
+FMCW_API fmcw_status fmcw_stft_frames(fmcw_handle* h, const fmcw_stft_out* sout);
+
 /* STFT of an arbitrary non-negative sequence x[L] (host or device): RP:270-299 on its own. */
 FMCW_API fmcw_status fmcw_stft(fmcw_handle* h, const float* x, uint64_t L, const fmcw_stft_out* sout);
 
@@ -158,8 +162,8 @@ FMCW_API fmcw_status fmcw_stft(fmcw_handle* h, const float* x, uint64_t L, const
  *   fmcw_process_frames -> fmcw_get_info (n_detected) -> all-gather counts ->
  *   fmcw_get_slow_time / fmcw_set_halo (neighbour exchange of window_length-1 samples) ->
  *   fmcw_stft_local_max -> all-reduce(max) -> fmcw_stft_sharded. */
-FMCW_API fmcw_status fmcw_get_slow_time(fmcw_handle* h, float* dst, uint64_t first, uint64_t count);
-FMCW_API fmcw_status fmcw_set_halo(fmcw_handle* h, const float* src, uint64_t count);
+FMCW_API fmcw_status fmcw_get_slow_time(fmcw_handle* h, double* dst, uint64_t first, uint64_t count);
+FMCW_API fmcw_status fmcw_set_halo(fmcw_handle* h, const double* src, uint64_t count);
 FMCW_API fmcw_status fmcw_stft_local_max(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset,
                                          double* pmax_raw_local);
 FMCW_API fmcw_status fmcw_stft_sharded(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset,
@@ -168,11 +172,11 @@ FMCW_API fmcw_status fmcw_stft_sharded(fmcw_handle* h, uint64_t L_total, uint64_
 /* Asynchronous form of the sharded path: every hand-off stays in device memory, the host only enqueues.
  *   fmcw_process_frames (device buffers) -> fmcw_shard_pack(msg) -> all-gather(msg) -> fmcw_shard_plan(gathered,
  *   world, rank, local_max) -> all-reduce(max, local_max) -> fmcw_shard_stft(global_max, out).
- * msg: float[2 + window_length-1] = {L_local & 0xFFFFF, L_local >> 20, first window_length-1 samples};
+ * msg: double[1 + window_length-1] = {L_local, first window_length-1 samples} (the slow-time signal is float64);
  * gathered: the world messages in rank order.  All pointers are device memory; work is queued on the
  * handle's stream (order it against the collective's stream with events). */
-FMCW_API fmcw_status fmcw_shard_pack(fmcw_handle* h, float* msg_dev);
-FMCW_API fmcw_status fmcw_shard_plan(fmcw_handle* h, const float* gathered_dev, uint32_t world, uint32_t rank,
+FMCW_API fmcw_status fmcw_shard_pack(fmcw_handle* h, double* msg_dev);
+FMCW_API fmcw_status fmcw_shard_plan(fmcw_handle* h, const double* gathered_dev, uint32_t world, uint32_t rank,
                                      double* local_max_dev);
 FMCW_API fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const fmcw_stft_out* sout);
 

@@ -15,7 +15,7 @@ def _worker(rank, world, port, lengths, win, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        full = torch.arange(sum(lengths), dtype=torch.float32) * 0.5 + 1.0        # the global slow-time signal
+        full = torch.arange(sum(lengths), dtype=torch.float64) * 0.5 + 1.0        # the global slow-time signal
         off = sum(lengths[:rank])
         x = full[off:off + lengths[rank]]
         lay = D.exchange_heads(x[:win - 1].contiguous(), lengths[rank], win)

@@ -108,7 +108,7 @@ def test_sharded_stft_equals_single_gpu(split):
         h = FmcwCuda(case["cfg"], case["calib"])
         h.process_frames(np.ascontiguousarray(case["iq"][f0:f0 + k]))
         L = h.info()["L_local"]
-        head = np.zeros(min(L, win - 1), dtype=np.float32)
+        head = np.zeros(min(L, win - 1), dtype=np.float64)
         if head.size:
             h.get_slow_time(head, 0, head.size)
         hs.append(h); Ls.append(L); heads.append(head)
@@ -118,7 +118,7 @@ def test_sharded_stft_equals_single_gpu(split):
     offs = np.concatenate([[0], np.cumsum(Ls)[:-1]]).astype(int)
     maxes = []
     for r, h in enumerate(hs):
-        halo = np.concatenate(heads[r + 1:] + [np.zeros(0, np.float32)])[:win - 1].astype(np.float32)
+        halo = np.concatenate(heads[r + 1:] + [np.zeros(0, np.float64)])[:win - 1].astype(np.float64)
         h.set_halo(np.ascontiguousarray(halo), halo.size)
         maxes.append(h.stft_local_max(L_total, int(offs[r])))
     pmax = max(maxes)
@@ -160,7 +160,7 @@ def test_async_sharded_path_equals_single_gpu(split):
             outs.append(h.process_frames(iq_d[f0:f0 + k].contiguous()))
         else:
             outs.append(h.process_frames(iq_d[:0].contiguous()))
-        msg = torch.zeros(2 + win - 1, dtype=torch.float32, device="cuda")
+        msg = torch.zeros(1 + win - 1, dtype=torch.float64, device="cuda")
         h.shard_pack(msg)
         h.synchronize()
         hs.append(h); msgs.append(msg)
