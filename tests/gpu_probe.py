@@ -41,3 +41,18 @@ for (NTS, PN, nf) in [(128, 64, 60), (64, 16, 80), (256, 256, 6)]:
     g = h.synth_frames(case["tables"], case["scene"].seed, 0)
     print(" synth mismatches", int((g != case["iq"]).sum()))
     h.close()
+
+# spectrogram error by level band (end to end)
+case = H.make_case(n_frames=60, NTS=128, PN=64)
+ref = H.oracle_no(case)
+h = FmcwCuda(case["cfg"], case["calib"])
+out, inten = h.run(case["iq"])
+nc = h.info()["ncol_local"]
+g = inten[:nc].T.astype(np.float64); r = ref["stft"]["intensity"]
+fin = np.isfinite(r) & np.isfinite(g)
+for lo, hi in [(-60, 1), (-100, -60), (-140, -100), (-180, -140), (-220, -180), (-260, -220), (-400, -260)]:
+    m = fin & (r > lo) & (r <= hi)
+    if m.any():
+        rel = np.abs(10 ** ((g[m] - r[m]) / 20) - 1)
+        print(f" band ({lo:4d},{hi:4d}] dB: n={m.sum():8d}  max |ddB|={np.abs(g[m]-r[m]).max():.2e}  max rel={rel.max():.2e}  p99.9 rel={np.quantile(rel,0.999):.2e}")
+h.close()

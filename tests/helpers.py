@@ -47,6 +47,14 @@ def db_errors(gpu_lin, ref_lin):
     return float(e_db), float(e_rel)
 
 
+def spectrogram_band_rel(gpu_db, ref_db, lo, hi):
+    """Max relative power error of the spectrogram bins whose reference level lies in (lo, hi] dB."""
+    g = np.asarray(gpu_db, dtype=np.float64)
+    r = np.asarray(ref_db, dtype=np.float64)
+    m = np.isfinite(r) & np.isfinite(g) & (r > lo) & (r <= hi)
+    return float(np.abs(10 ** ((g[m] - r[m]) / 20) - 1).max()) if m.any() else 0.0
+
+
 def spectrogram_errors(gpu_db, ref_db):
     """Spectrogram intensities are already 20*log10(P/max(P)) (RP:283).  Returns (max |err| dB where
     ref > -60 dB, max relative power error elsewhere)."""
