@@ -182,7 +182,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     sx, cfg, scene = build_workload(args.frames)
     n, PN, NTS, n_rx = args.frames, 64, 128, 3
-    h = FmcwCuda(cfg, synth.default_calib(n_rx, NTS) / 4095.0, device=local_rank)
+    h = FmcwCuda(cfg, synth.default_calib(n_rx, NTS) / 4095.0, device=local_rank, torch_stream_sync=False)
 
     # ---- synthetic input, generated on the device by the counter-based generator ----
     frame0 = rank * n

@@ -29,8 +29,14 @@ def _is_torch(a):
 class FmcwCuda:
     """One libfmcw_cuda handle (one GPU, one stream)."""
 
-    def __init__(self, cfg, calib_data=None, device: int = 0):
+    def __init__(self, cfg, calib_data=None, device: int = 0, torch_stream_sync: bool = True):
+        """``torch_stream_sync``: when torch CUDA tensors are passed, order the library's stream after torch's
+        current stream before each call and torch's current stream after the library's afterwards (stream-ordered
+        semantics; also what makes recycled caching-allocator blocks safe).  Callers that manage streams and
+        buffer lifetimes themselves (bench.py) switch it off."""
         self.lib = _lib.load()
+        self.torch_stream_sync = torch_stream_sync
+        self._ext_stream = None
         self.cfg = cfg
         self.c_cfg = to_c_config(cfg)
         self.device = device
@@ -119,6 +125,21 @@ class FmcwCuda:
         so.layout = layout
         return so
 
+    # ---- stream ordering against torch ----
+    def _order_before(self, ref):
+        if self.torch_stream_sync and _is_torch(ref) and ref.is_cuda:
+            import torch
+            if self._ext_stream is None:
+                self._ext_stream = torch.cuda.ExternalStream(self.stream, device=ref.device)
+            self._ext_stream.wait_stream(torch.cuda.current_stream(ref.device))
+            return ref.device
+        return None
+
+    def _order_after(self, dev):
+        if dev is not None:
+            import torch
+            torch.cuda.current_stream(dev).wait_stream(self._ext_stream)
+
     # ---- the chain ----
     def process_frames(self, iq, out: dict | None = None) -> dict:
         """RP:197-261 for every frame of ``iq`` (int16 [n][rx][PN][NTS][2])."""
@@ -126,7 +147,9 @@ class FmcwCuda:
         if out is None:
             out = self.alloc_frame_out(n, device=iq.device if _is_torch(iq) else None)
         fo = self._frame_struct(out)
+        dev = self._order_before(iq)
         self._check(self.lib.fmcw_process_frames(self._h, _ptr(iq), n, C.byref(fo)))
+        self._order_after(dev)
         return out
 
     def run(self, iq, out: dict | None = None, intensity=None, layout: int = _lib.LAYOUT_TIME_MAJOR):
@@ -145,7 +168,9 @@ class FmcwCuda:
                 intensity = torch.empty(shape, dtype=torch.float32, device=dev)
         fo = self._frame_struct(out)
         so = self._stft_struct(intensity, layout)
+        sdev = self._order_before(iq)
         self._check(self.lib.fmcw_run(self._h, _ptr(iq), n, C.byref(fo), C.byref(so)))
+        self._order_after(sdev)
         return out, intensity
 
     def stft_frames(self, n_frames: int, intensity=None, layout: int = _lib.LAYOUT_TIME_MAJOR):
@@ -170,7 +195,9 @@ class FmcwCuda:
             else:
                 intensity = np.empty(shape, dtype=np.float32)
         so = self._stft_struct(intensity, layout)
+        sdev = self._order_before(x)
         self._check(self.lib.fmcw_stft(self._h, _ptr(x), L, C.byref(so)))
+        self._order_after(sdev)
         return intensity
 
     def stft_axes(self, L_total: int, col_begin: int = 0, ncol: int | None = None):
@@ -210,14 +237,20 @@ class FmcwCuda:
 
     # ---- asynchronous sharded path (device-side hand-offs) ----
     def shard_pack(self, msg):
+        dev = self._order_before(msg)
         self._check(self.lib.fmcw_shard_pack(self._h, _ptr(msg)))
+        self._order_after(dev)
 
     def shard_plan(self, gathered, world: int, rank: int, local_max):
+        dev = self._order_before(gathered)
         self._check(self.lib.fmcw_shard_plan(self._h, _ptr(gathered), world, rank, _ptr(local_max)))
+        self._order_after(dev)
 
     def shard_stft(self, global_max, intensity, layout: int = _lib.LAYOUT_TIME_MAJOR):
         so = self._stft_struct(intensity, layout)
+        dev = self._order_before(global_max)
         self._check(self.lib.fmcw_shard_stft(self._h, _ptr(global_max), C.byref(so)))
+        self._order_after(dev)
         return intensity
 
     # ---- extras ----

@@ -1,0 +1,86 @@
+"""Full-size parity (BASELINE.json configs[1]: 5,000 frames, 3 RX, 64 x 128, hop-1 STFT on one GPU) through
+size-independent checks: sampled frames and sampled spectrogram columns against the oracle, the exact global
+normalisation, and structural properties of the whole 1.3 GB output."""
+import numpy as np
+import pytest
+
+from fmcw_radar_processing_b200 import synth
+from fmcw_radar_processing_b200.config import fmcw_configurations
+from fmcw_radar_processing_b200.parse import make_sxml
+from oracle import fmcw_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    import torch
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    n, n_rx, PN, NTS = 5000, 3, 64, 128
+    sx = make_sxml(numSamplesPerChirp=NTS, numChirpsPerFrame=PN, numAntennasRx=n_rx)
+    cfg = fmcw_configurations(sx)
+    scene = synth.scene_c2(seed=2)
+    tab = synth.scene_tables(scene, cfg["dist_per_bin"], 256, cfg["PRT"], cfg["lambda"], 0, n)
+    h = FmcwCuda(cfg, synth.default_calib(n_rx, NTS) / 4095.0)
+    iq = torch.empty((n, n_rx, PN, NTS, 2), dtype=torch.int16, device="cuda")
+    h.synth_frames(tab, scene.seed, 0, sigma=scene.sigma, dc=scene.dc, rx_step=scene.rx_step, out=iq)
+    out, inten = h.run(iq)
+    h.synchronize()
+    info = h.info()
+    x = np.empty(info["L_total"], dtype=np.float64)
+    h.get_slow_time(x, 0, x.size)
+    yield dict(h=h, sx=sx, cfg=cfg, scene=scene, tab=tab, iq=iq, out=out, inten=inten, info=info, x=x)
+    h.close()
+
+
+def test_sampled_frames_match_oracle(c2):
+    ocfg = O.configure(c2["sx"])
+    cal = O.calib_rx1(synth.default_calib(3, 128) / 4095.0, ocfg)
+    out = {k: v.cpu().numpy() for k, v in c2["out"].items()}
+    for f in (0, 17, 1234, 2500, 4999):
+        iq_f = synth.synth_frames(c2["tab"][f:f + 1], c2["scene"].seed, f, 3, 64, 128)
+        assert np.array_equal(iq_f[0], c2["iq"][f].cpu().numpy())            # device generator == NumPy generator
+        frames, _, _, _ = O.f_parse_data2(iq_f, synth.default_calib(3, 128), c2["sx"])
+        fo = O.process_frame(frames[0], cal, ocfg)
+        assert out["detected"][f] == 1 and out["range_bin"][f] == fo.tgt_range_idx[0] - 1
+        assert out["doppler_bin"][f] == fo.tgt_doppler_idx[0] - 1
+        assert np.abs(20 * np.log10(out["range_max_abs"][f] / fo.range_max)).max() < 1e-2     # all 256 bins
+        strong = fo.range_max > fo.range_max.max() * 1e-3
+        assert np.abs(20 * np.log10(out["range_max_abs"][f][strong] / fo.range_max[strong])).max() < 1e-3
+        assert np.allclose(c2["x"][f * 64:(f + 1) * 64], np.abs(fo.slow_time_row), rtol=1e-9)   # float64 slow-time row
+
+
+def test_sizes_and_exact_normalisation(c2):
+    info = c2["info"]
+    assert info["n_detected"] == 5000 and info["L_total"] == 320000 and info["nfft"] == 2 ** 19
+    assert info["ncol_total"] == info["ncol_local"] == 319981
+    ocfg = O.configure(c2["sx"])
+    from scipy.signal import windows
+    pm = O.stft_global_max(c2["x"], windows.kaiser(20, 3.0, sym=True), 2 ** 19, 1, 319981)
+    assert info["pmax_raw"] == pytest.approx(pm, rel=1e-6)
+
+
+def test_sampled_columns_match_oracle(c2):
+    ocfg = O.configure(c2["sx"])
+    pm = c2["info"]["pmax_raw"]
+    for c0 in (0, 159000, 319981 - 300):
+        ref = O.stft_restated(c2["x"], ocfg, pmax_raw=pm, col_range=(c0, c0 + 300))
+        got = c2["inten"][c0:c0 + 300].cpu().numpy().T.astype(np.float64)
+        r = ref["intensity"]
+        strong = r > -60
+        assert np.abs(got[strong] - r[strong]).max() < 1e-3
+        band = (r > -120) & (r <= -60)
+        assert np.abs(10 ** ((got[band] - r[band]) / 20) - 1).max() < 1e-4
+
+
+def test_whole_output_structure(c2):
+    import torch
+    inten = c2["inten"][:319981]
+    assert bool(torch.isfinite(inten).all())
+    assert float(inten.max()) <= 1e-4                     # normalised by the global maximum: nothing above 0 dB
+    assert float(inten.max()) > -0.5                      # and the maximum itself is reached (at the lowest frequencies)
+    # checksum of checksums: per-column sums in float64 are reproducible between two runs (deterministic kernels)
+    s1 = inten.double().sum(dim=1)
+    out2, inten2 = c2["h"].run(c2["iq"])
+    c2["h"].synchronize()
+    assert torch.equal(inten2[:319981].double().sum(dim=1), s1)
