@@ -24,7 +24,7 @@ def api():
 
 
 SHAPES = [(128, 64, 1, 48, 1), (64, 16, 2, 90, 1), (256, 256, 1, 5, 1), (128, 64, 3, 30, 2), (96, 24, 1, 40, 1),
-          (512, 8, 1, 12, 1)]
+          (512, 8, 1, 12, 1), (256, 256, 4, 3, 4)]       # the last one is the C4 shape (4 RX x 256 x 256)
 
 
 @pytest.mark.parametrize("NTS,PN,n_rx,nf,rx_sel", SHAPES)
@@ -195,3 +195,25 @@ def test_error_paths(api):
         h.stft(np.ones(5, dtype=np.float32))
     assert ei.value.status == 8
     h.close()
+
+
+@pytest.mark.parametrize("win,overlap_pct", [(32, 50), (64, 75), (128, 90), (256, 50), (32, 90)])
+def test_fleet_window_hop_sweep(api, win, overlap_pct):
+    """C5: independent radars (own history, own nfft, own max), STFT window 32-256 at 50-90 % overlap:
+    hop = window - floor(window * overlap)."""
+    ov = (win * overlap_pct) // 100
+    for seed in (1000, 1001, 1002):
+        case = H.make_case(n_frames=40 + 5 * (seed - 1000), NTS=128, PN=64, seed=seed, window_length=win, overlap=ov)
+        ref = H.oracle_no(case)
+        h = api(case["cfg"], case["calib"])
+        out, inten = h.run(case["iq"])
+        info = h.info()
+        st = ref["stft"]
+        nc = info["ncol_local"]
+        assert nc == st["intensity"].shape[1] and info["nfft"] == st["nfft"]
+        assert info["pmax_raw"] == pytest.approx(st["pmax_raw"], rel=2e-6)
+        e_db, _ = H.spectrogram_errors(inten[:nc].T, st["intensity"])
+        assert e_db < TOL_DB
+        T, F, _, _ = h.stft_axes(info["L_total"])
+        assert np.allclose(T, st["T"], rtol=1e-14) and np.allclose(F, st["frequency"], rtol=1e-14)
+        h.close()
