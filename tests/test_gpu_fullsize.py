@@ -84,3 +84,50 @@ def test_whole_output_structure(c2):
     out2, inten2 = c2["h"].run(c2["iq"])
     c2["h"].synchronize()
     assert torch.equal(inten2[:319981].double().sum(dim=1), s1)
+
+
+def test_c3_streaming_200k_frames():
+    """BASELINE.json configs[2]: 200,000 frames of the reference shape in one fused call on one GPU
+    (6.5 GB of samples in, 12.8 M spectrogram columns = 52 GB out, nfft = 2^24)."""
+    import torch
+    from scipy.signal import windows
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    if torch.cuda.mem_get_info()[0] < 80e9:
+        pytest.skip("needs ~65 GB of free HBM")
+    n, PN, NTS = 200_000, 64, 128
+    sx = make_sxml(numSamplesPerChirp=NTS, numChirpsPerFrame=PN, numAntennasRx=1)
+    cfg = fmcw_configurations(sx)
+    scene = synth.scene_c1(seed=3)
+    tab = synth.scene_tables(scene, cfg["dist_per_bin"], 256, cfg["PRT"], cfg["lambda"], 0, n)
+    h = FmcwCuda(cfg, synth.default_calib(1, NTS) / 4095.0)
+    iq = torch.empty((n, 1, PN, NTS, 2), dtype=torch.int16, device="cuda")
+    h.synth_frames(tab, scene.seed, 0, sigma=scene.sigma, dc=scene.dc, rx_step=scene.rx_step, out=iq)
+    out = h.alloc_frame_out(n, device="cuda")
+    inten = torch.empty((h.max_cols(n), 1024), dtype=torch.float32, device="cuda")
+    h.run(iq, out, inten)
+    h.synchronize()
+    info = h.info()
+    assert info["n_detected"] == n and info["L_total"] == n * PN and info["nfft"] == 2 ** 24
+    assert info["ncol_local"] == n * PN - 19
+    x = np.empty(info["L_total"], dtype=np.float64)
+    h.get_slow_time(x, 0, x.size)
+    # exact global maximum: the bound 2*S(0)^2 singles out the candidate columns; full-grid FFT of those
+    w = windows.kaiser(20, 3.0, sym=True)
+    s0 = np.convolve(x, w[::-1], mode="valid")                    # sum_n w[n] x[t+n] (x >= 0)
+    order = np.argsort(-s0)[:4]
+    best = 0.0
+    for t in order:
+        if 2 * s0[t] ** 2 <= best:
+            break
+        p = np.abs(np.fft.rfft(x[t:t + 20] * w, 2 ** 24)) ** 2
+        p[1:-1] *= 2
+        best = max(best, float(p.max()))
+    assert info["pmax_raw"] == pytest.approx(best, rel=1e-6)
+    ocfg = O.configure(sx)
+    for c0 in (0, 6_400_000, n * PN - 19 - 200):
+        ref = O.stft_restated(x, ocfg, pmax_raw=best, col_range=(c0, c0 + 200))
+        got = inten[c0:c0 + 200].cpu().numpy().T.astype(np.float64)
+        strong = ref["intensity"] > -60
+        assert np.abs(got[strong] - ref["intensity"][strong]).max() < 1e-3
+    assert bool(torch.isfinite(inten[::4096]).all())
+    h.close()
