@@ -14,8 +14,19 @@
 
 namespace fmcw {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as one packed FADD2 (sm_100 f32x2 pipe)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  float2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return r;
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -27,16 +38,16 @@ __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2&
   float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
   a0 = cadd(s02, s13);
   a2 = csub(s02, s13);
-  a1 = cadd(d02, mul_mj(d13));
-  a3 = cadd(d02, mul_pj(d13));
+  a1 = make_float2(d02.x + d13.y, d02.y - d13.x);     // d02 + (-j) d13
+  a3 = make_float2(d02.x - d13.y, d02.y + d13.x);     // d02 + (+j) d13
 }
 // same with a2 = a3 = 0 / with a1 = a2 = a3 = 0 (zero padding of the range FFT)
 __device__ __forceinline__ void dft4_z2(float2& a0, float2& a1, float2& a2, float2& a3) {
   float2 x0 = a0, x1 = a1;
   a0 = cadd(x0, x1);
   a2 = csub(x0, x1);
-  a1 = cadd(x0, mul_mj(x1));
-  a3 = cadd(x0, mul_pj(x1));
+  a1 = make_float2(x0.x + x1.y, x0.y - x1.x);
+  a3 = make_float2(x0.x - x1.y, x0.y + x1.x);
 }
 __device__ __forceinline__ void dft4_z1(float2& a0, float2& a1, float2& a2, float2& a3) { a1 = a0; a2 = a0; a3 = a0; }
 
