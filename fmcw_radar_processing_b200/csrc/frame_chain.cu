@@ -137,21 +137,47 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
     for (int i = 0; i < 16; ++i) mx[i] = 0.f;
 
     // ================= pass 1: range FFT of every chirp, running max of |X|^2 =================
+    // software pipelining: the samples of the next chirp pair are requested before this pair's FFT
+    constexpr bool PF = (NZ <= 2);       // (the 16-word prefetch of NZ = 4 would spill)
+    uint32_t wnext[4 * NZ];
+    if (PF) {
+      const uint32_t c = warp * 2 + half;
+      const uint32_t* cb = fbase + (uint64_t)(c < PN ? c : 0) * NTS;
+#pragma unroll
+      for (int r = 0; r < 4 * NZ; ++r) {
+        const uint32_t n = s + 16 * r;
+        wnext[r] = (c < PN && n < NTS) ? __ldg(cb + n) : 0u;
+      }
+    }
     for (uint32_t pair = warp; pair * 2 < PN; pair += CHAIN_WARPS) {
       const uint32_t c = pair * 2 + half;
       const bool active = c < PN;
       const uint32_t* cb = fbase + (uint64_t)(active ? c : 0) * NTS;
       int ci[4 * NZ], cq[4 * NZ];
       int sumI = 0, sumQ = 0;
+      if (!PF) {
+#pragma unroll
+        for (int r = 0; r < 4 * NZ; ++r) {
+          const uint32_t n = s + 16 * r;
+          wnext[r] = (active && n < NTS) ? __ldg(cb + n) : 0u;
+        }
+      }
 #pragma unroll
       for (int r = 0; r < 4 * NZ; ++r) {
-        const uint32_t n = s + 16 * r;
-        uint32_t w = 0;
-        if (active && n < NTS) w = __ldg(cb + n);
+        const uint32_t w = wnext[r];
         ci[r] = (int)(short)(w & 0xffffu);
         cq[r] = (int)w >> 16;
         sumI += ci[r];
         sumQ += cq[r];
+      }
+      if (PF) {
+        const uint32_t cn = (pair + CHAIN_WARPS) * 2 + half;
+        const uint32_t* cbn = fbase + (uint64_t)(cn < PN ? cn : 0) * NTS;
+#pragma unroll
+        for (int r = 0; r < 4 * NZ; ++r) {
+          const uint32_t n = s + 16 * r;
+          wnext[r] = (cn < PN && n < NTS) ? __ldg(cbn + n) : 0u;
+        }
       }
       if (active)
         for (uint32_t n = s + NR; n < NTS; n += 16) {   // samples past the FFT length still enter the mean (RP:204)
