@@ -30,15 +30,34 @@ namespace {
 
 constexpr float K_DB = 6.020599913279624f;
 constexpr int TC_HALF = 10, TC_KP = 16;
-constexpr int TC_M = 128, TC_N = 128;
-constexpr int TC_MAT_BYTES = TC_N * TC_KP * 4;       // 8 KB per operand matrix
-constexpr int TC_B_BYTES = 4 * TC_MAT_BYTES;         // Chi | Clo | Shi | Slo
-constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
-constexpr int TC_STEP = TC_N - 1;              // new bin positions per chunk (one position of overlap)
+constexpr int TC_M = 128;
+constexpr int TC_A_MAT_BYTES = TC_M * TC_KP * 4;     // 8 KB per A operand matrix
 constexpr int TC_QF = 16;
-constexpr int TC_DBS = 130;                     // dB row stride: 8-byte aligned rows, conflict-free 64-bit column-wise stores
-constexpr int TC_SMEM_BAR_OFF = 2 * 4 * TC_MAT_BYTES + 2 * TC_B_BYTES + (MAX_NQ + 32 + MAX_NQ + 32 + 4 * 32 * TC_DBS + 3) / 4 * 4 * 4;
+
+// Kernel shape: BN bins per chunk (the N of the UMMA tile), EW epilogue warps, CTAS resident CTAs per SM.
+//   <128, 16, 1>: one CTA per SM, everything double buffered;
+//   < 64,  8, 2>: two independent CTAs per SM, so that one CTA's dB phase (XU bound) overlaps the other's
+//                 interp1 / store phase (LSU bound) -- the default.
+template <int BN_, int EW_, int CTAS_>
+struct TcShape {
+  static constexpr int BN = BN_, EW = EW_, CTAS = CTAS_;
+  static constexpr int SW = EW / 4;                    // warps per TMEM lane quarter
+  static constexpr int CW = 32 / SW;                   // spectrogram columns per warp in the interp1 phase
+  static constexpr int THREADS = (EW + 2) * 32;
+  static constexpr int STEP = BN - 1;                  // new bin positions per chunk (one position of overlap)
+  static constexpr int B_MAT_BYTES = BN * TC_KP * 4;
+  static constexpr int B_BYTES = 4 * B_MAT_BYTES;      // Chi | Clo | Shi | Slo
+  static constexpr int ABUF = (CTAS == 1) ? 2 : 1;     // A tile buffers
+  static constexpr int DBS = BN + 2;                   // dB row stride: 8-byte aligned, conflict-free both ways
+  static constexpr int TMEM_COLS = 4 * BN;             // two stages of (Re | Im)
+  static constexpr int OFF_B = ABUF * 4 * TC_A_MAT_BYTES;
+  static constexpr int OFF_AQ = OFF_B + 2 * B_BYTES;
+  static constexpr int N_F32 = MAX_NQ + 32 + MAX_NQ + 64 + 4 * 32 * DBS;
+  static constexpr int OFF_BAR = OFF_AQ + ((N_F32 + 3) / 4) * 16;
+  static constexpr int SMEM = OFF_BAR + 16 * 8 + 16;
+};
+static_assert(TcShape<128, 16, 1>::BN / TcShape<128, 16, 1>::SW == 32 && TcShape<64, 8, 2>::BN / TcShape<64, 8, 2>::SW == 32,
+              "every epilogue warp converts 32 bins of a chunk");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -142,25 +161,26 @@ __device__ __forceinline__ void flush_rows(uint32_t a_stage, int ncols_valid, fl
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// B operands: chunk c covers bin positions [c*127, c*127+128) (one position of overlap, so that every chunk
-// carries the bin preceding its first new bin: the lower bracket of the first interp1 interval); per chunk
-// the matrices Chi | Clo | Shi | Slo in the UMMA layout; per position one packed word
-// {bit 31: one-sided doubling, bits 12..23: first query completed by this position, bits 0..11: count}
+// B operands: chunk c covers bin positions [c*(BN-1), c*(BN-1)+BN) (one position of overlap, so that every
+// chunk carries the bin preceding its first new bin: the lower bracket of the first interp1 interval); per chunk
+// the matrices Chi | Clo | Shi | Slo in the UMMA layout
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, StftGeom g, float* __restrict__ tcB,
-                                                              uint32_t* __restrict__ tc_meta, int n_chunk_cap) {
+__global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, StftGeom g, float* __restrict__ tcB, int BN,
+                                                              int n_chunk_cap) {
   const StftPlan* P = t.plan;
   if (P->valid <= 0) return;
   const int nb = P->nb;
-  const int n_chunks = (nb - 1 + TC_STEP - 1) / TC_STEP;
+  const int step = BN - 1;
+  const int n_chunks = (nb - 1 + step - 1) / step;
   if (n_chunks > n_chunk_cap) return;
   const unsigned long long nfft = P->nfft;
   const long long mod = (long long)(2 * nfft);
-  const int total = n_chunks * TC_N * TC_KP;
+  const int total = n_chunks * BN * TC_KP;
+  const int mat = BN * TC_KP;                    // floats per operand matrix
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % TC_KP, idx = i / TC_KP;
-    const int ch = idx / TC_N, n = idx % TC_N;
-    const int pos = ch * TC_STEP + n;
+    const int ch = idx / BN, n = idx % BN;
+    const int pos = ch * step + n;
     double cv = 0.0, sv = 0.0;
     if (pos < nb) {
       const long long bin = t.bins[pos];
@@ -177,43 +197,35 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
     }
     const float chi = tf32_rna((float)cv), shi = tf32_rna((float)sv);
     const float clo = tf32_rna((float)(cv - (double)chi)), slo = tf32_rna((float)(sv - (double)shi));
-    float* blk = tcB + (size_t)ch * (TC_B_BYTES / 4);
+    float* blk = tcB + (size_t)ch * (4 * mat);
     const int off = tc_off_floats(n, k);
     blk[off] = chi;
-    blk[TC_MAT_BYTES / 4 + off] = clo;
-    blk[2 * (TC_MAT_BYTES / 4) + off] = shi;
-    blk[3 * (TC_MAT_BYTES / 4) + off] = slo;
-    if (k == 0) {
-      uint32_t w = 0;
-      if (pos < nb) {
-        const int qs = pos > 0 ? t.qend[pos - 1] : 0;
-        const int cnt = pos > 0 ? t.qend[pos] - qs : 0;
-        w = (t.kcb[pos] > 0.f ? 0x80000000u : 0u) | ((uint32_t)qs << 12) | (uint32_t)cnt;
-      }
-      tc_meta[idx] = w;
-    }
+    blk[mat + off] = clo;
+    blk[2 * mat + off] = shi;
+    blk[3 * mat + off] = slo;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// main kernel: one CTA per SM, 16 epilogue warps + MMA issuer + bulk-copy producer
+// main kernel: EW epilogue warps + MMA issuer + bulk-copy producer
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT, int NQC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int LAYOUT, int NQC, class S>
+__global__ void __launch_bounds__(S::THREADS, S::CTAS)
 stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
-               const uint32_t* __restrict__ tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err,
-               int dbg_mode, const double* __restrict__ gmax_dev) {
+               unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, int dbg_mode,
+               const double* __restrict__ gmax_dev) {
+  constexpr int BN = S::BN, EW = S::EW, SW = S::SW, CW = S::CW, STEP = S::STEP, DBS = S::DBS, ABUF = S::ABUF;
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
   extern __shared__ __align__(128) unsigned char smem[];
-  float* sA = reinterpret_cast<float*>(smem);                                       // 2 x (Ehi | Elo | Ohi | Olo)
-  float* sB = reinterpret_cast<float*>(smem + 2 * 4 * TC_MAT_BYTES);                // 2 x (Chi | Clo | Shi | Slo)
-  float* s_aq = reinterpret_cast<float*>(smem + 2 * 4 * TC_MAT_BYTES + 2 * TC_B_BYTES);   // [MAX_NQ]
-  float* s_ws = s_aq + MAX_NQ;                                                      // [32]
-  int* s_qpos = reinterpret_cast<int*>(s_ws + 32);                                  // [MAX_NQ] position of each query's lower bracket
-  int* s_qrng = s_qpos + MAX_NQ;                                                    // [32] first query of every chunk
-  float* s_db = reinterpret_cast<float*>(s_qrng + 32);                              // [4 quarters][32 columns][TC_DBS] dB of a chunk
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TC_SMEM_BAR_OFF);
+  float* sA = reinterpret_cast<float*>(smem);                          // ABUF x (Ehi | Elo | Ohi | Olo)
+  float* sB = reinterpret_cast<float*>(smem + S::OFF_B);               // 2 x (Chi | Clo | Shi | Slo)
+  float* s_aq = reinterpret_cast<float*>(smem + S::OFF_AQ);            // [MAX_NQ] interp1 weights
+  float* s_ws = s_aq + MAX_NQ;                                         // [32] normalised window
+  int* s_qpos = reinterpret_cast<int*>(s_ws + 32);                     // [MAX_NQ] position of each query's lower bracket
+  int* s_qrng = s_qpos + MAX_NQ;                                       // [64] first query of every chunk
+  float* s_db = reinterpret_cast<float*>(s_qrng + 64);                 // [4 quarters][32 columns][DBS] dB of a chunk
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -221,7 +233,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   const unsigned long long ncl = ce - cb;
   if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
   const int nq = P->nq, nb = P->nb;
-  const int n_chunks = (nb - 1 + TC_STEP - 1) / TC_STEP;
+  const int n_chunks = (nb - 1 + STEP - 1) / STEP;
   const unsigned long long n_tiles = (ncl + TC_M - 1) / TC_M;
   // normalisation max(P): the plan's own search, or the all-reduced value of a sharded run
   const double pmax = gmax_dev ? *gmax_dev : P->pmax_raw;
@@ -232,19 +244,19 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   auto BAR = [&](int i) { return bar0 + (uint32_t)(i * 8); };
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(0 + i), TC_EPI_WARPS * 32); mbar_init(BAR(2 + i), 1);
+      mbar_init(BAR(0 + i), EW * 32); mbar_init(BAR(2 + i), 1);
       mbar_init(BAR(4 + i), 1); mbar_init(BAR(6 + i), 1);
-      mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), TC_EPI_WARPS * 32);
+      mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), EW * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  if (warp == TC_EPI_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)));
+  if (warp == EW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(S::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < nq; i += TC_THREADS) { s_aq[i] = t.aq[i]; s_qpos[i] = t.qpos[i]; }
-  if (tid <= n_chunks && tid < 32) {   // queries [s_qrng[ch], s_qrng[ch+1]) have their bracket inside chunk ch
-    const int p = tid * TC_STEP;
+  for (int i = tid; i < nq; i += S::THREADS) { s_aq[i] = t.aq[i]; s_qpos[i] = t.qpos[i]; }
+  if (tid <= n_chunks && tid < 64) {   // queries [s_qrng[ch], s_qrng[ch+1]) have their bracket inside chunk ch
+    const int p = tid * STEP;
     s_qrng[tid] = t.qend[p < nb ? p : nb];
   }
   if (tid < 2 * TC_HALF) s_ws[tid] = (float)((double)t.win[tid] / sqrt(pmax));
@@ -253,53 +265,56 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < TC_EPI_WARPS) {
-    // ============ epilogue warps: lane quarter qd = warp & 3 (TMEM lanes 32*qd..), sub-warp sw = warp >> 2 ============
+  if (warp < EW) {
+    // ====== epilogue warps: lane quarter qd = warp & 3 (TMEM lanes 32*qd..), sub-warp sw = warp >> 2 ======
     const int qd = warp & 3, sw = warp >> 2;
     const int m = qd * 32 + lane;                         // row of the tile = spectrogram column = TMEM lane
     const uint32_t a_aq = smem_u32(s_aq), a_qpos = smem_u32(s_qpos);
-    const uint32_t a_db = smem_u32(s_db) + (uint32_t)(qd * 32 * TC_DBS * 4);      // dB rows of this quarter's 32 columns
+    const uint32_t a_db = smem_u32(s_db) + (uint32_t)(qd * 32 * DBS * 4);      // dB rows of this quarter's 32 columns
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
     const float inv = (float)(1.0 / sqrt(pmax));
     // the only positions without the one-sided doubling: bin 0 (if planned) and the Nyquist bin
     const int sp0 = (t.bins[0] == 0) ? 0 : -1;
     const int sp1 = ((unsigned long long)t.bins[nb - 1] == P->nfft / 2) ? nb - 1 : -1;
 
-    // A operands of one column: mean removed, windowed, folded even/odd, split hi/lo; this warp writes matrix `sw`
+    // A operands of one column: mean removed in float64, windowed, folded even/odd, split hi/lo.  The SW warps of a
+    // quarter share the work: this warp writes 4/SW of the four matrices Ehi | Elo | Ohi | Olo.
     auto build_a = [&](unsigned long long tile, int buf) {
       unsigned long long col = cb + tile * TC_M + m;
       if (col >= ce) col = ce - 1;
       const sig_t* xs = x + (col * g.hop - off);
-      // float64 samples: the mean is removed in float64, only the small residual is rounded to float32
       double xd[2 * TC_HALF];
       double mean_d = 0.0;
 #pragma unroll
       for (int n = 0; n < 2 * TC_HALF; ++n) { xd[n] = __ldg(xs + n); mean_d += xd[n]; }
       mean_d *= (1.0 / (2 * TC_HALF));
       const float mean = (float)mean_d;        // the DC tap carries the float32 mean; its rounding error joins the residual
-      float xv[2 * TC_HALF];
+      float yv[2 * TC_HALF];
 #pragma unroll
-      for (int n = 0; n < 2 * TC_HALF; ++n) xv[n] = (float)(xd[n] - (double)mean);
-      float v[TC_KP];
+      for (int n = 0; n < 2 * TC_HALF; ++n) yv[n] = s_ws[n] * (float)(xd[n] - (double)mean);
 #pragma unroll
-      for (int k = 0; k < TC_HALF; ++k) {
-        const float ylo = s_ws[TC_HALF - 1 - k] * xv[TC_HALF - 1 - k], yhi = s_ws[TC_HALF + k] * xv[TC_HALF + k];
-        v[k] = (sw < 2) ? (ylo + yhi) : (ylo - yhi);
-      }
-      v[TC_HALF] = (sw < 2) ? mean * inv : 0.f;           // DC tap: multiplies the tabulated window response
+      for (int mi = 0; mi < 4 / SW; ++mi) {
+        const int mat = sw * (4 / SW) + mi;                // 0 Ehi, 1 Elo, 2 Ohi, 3 Olo
+        const bool even = mat < 2, lo = (mat & 1) != 0;
+        float v[TC_KP];
 #pragma unroll
-      for (int k = TC_HALF + 1; k < TC_KP; ++k) v[k] = 0.f;
-      float* rowp = sA + buf * (4 * TC_MAT_BYTES / 4) + sw * (TC_MAT_BYTES / 4) + (m >> 3) * (TC_KP * 8) + (m & 7) * 4;
+        for (int k = 0; k < TC_HALF; ++k)
+          v[k] = even ? (yv[TC_HALF - 1 - k] + yv[TC_HALF + k]) : (yv[TC_HALF - 1 - k] - yv[TC_HALF + k]);
+        v[TC_HALF] = even ? mean * inv : 0.f;               // DC tap: multiplies the tabulated window response
 #pragma unroll
-      for (int kc = 0; kc < TC_KP / 4; ++kc) {
-        float4 o4;
-        float* op = &o4.x;
+        for (int k = TC_HALF + 1; k < TC_KP; ++k) v[k] = 0.f;
+        float* rowp = sA + buf * (4 * TC_A_MAT_BYTES / 4) + mat * (TC_A_MAT_BYTES / 4) + (m >> 3) * (TC_KP * 8) + (m & 7) * 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float hi = tf32_rna(v[4 * kc + j]);
-          op[j] = (sw & 1) ? tf32_rna(v[4 * kc + j] - hi) : hi;
+        for (int kc = 0; kc < TC_KP / 4; ++kc) {
+          float4 o4;
+          float* op = &o4.x;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float hi = tf32_rna(v[4 * kc + j]);
+            op[j] = lo ? tf32_rna(v[4 * kc + j] - hi) : hi;
+          }
+          *reinterpret_cast<float4*>(rowp + kc * 32) = o4;
         }
-        *reinterpret_cast<float4*>(rowp + kc * 32) = o4;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
       mbar_arrive(BAR(0 + buf));
@@ -309,7 +324,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
     if (blockIdx.x < n_tiles) build_a(blockIdx.x, 0);
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const unsigned long long next = tile + gridDim.x;
-      if (next < n_tiles) {                               // A of the next tile while this tile's chunks are in flight
+      if (ABUF == 2 && next < n_tiles) {                  // A of the next tile while this tile's chunks are in flight
         const int nbuf = (int)((it + 1) & 1);
         mbar_wait(BAR(2 + nbuf), (uint32_t)((((it + 1) >> 1) & 1) ^ 1));
         build_a(next, nbuf);
@@ -322,13 +337,13 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
       for (int ch = 0; ch < n_chunks; ++ch) {
         const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
         const int ts = (int)(cseq & 1);
-        const int gi = (sw + ch) & 3;                       // 32-bin group of this chunk converted to dB by this warp
-        const int pos_c0 = ch * TC_STEP;                    // bin position of chunk column 0
+        const int gi = (sw + ch) % SW;                      // 32-bin group of this chunk converted to dB by this warp
+        const int pos_c0 = ch * STEP;                       // bin position of chunk column 0
         mbar_wait(BAR(8 + ts), (uint32_t)((cseq >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
           float re[32], im[32];
-          const uint32_t c0 = (uint32_t)(ts * 2 * TC_N + gi * 32);
+          const uint32_t c0 = (uint32_t)(ts * 2 * BN + gi * 32);
           float a16[16];
           tmem_ld16(t_lane + c0, a16);
 #pragma unroll
@@ -336,22 +351,22 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           tmem_ld16(t_lane + c0 + 16, a16);
 #pragma unroll
           for (int j = 0; j < 16; ++j) re[16 + j] = a16[j];
-          tmem_ld16(t_lane + c0 + TC_N, a16);
+          tmem_ld16(t_lane + c0 + BN, a16);
 #pragma unroll
           for (int j = 0; j < 16; ++j) im[j] = a16[j];
-          tmem_ld16(t_lane + c0 + TC_N + 16, a16);
+          tmem_ld16(t_lane + c0 + BN + 16, a16);
 #pragma unroll
           for (int j = 0; j < 16; ++j) im[16 + j] = a16[j];
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(BAR(10 + ts));                        // accumulators are in registers: TMEM stage back to the MMA warp
           if (dbg_mode == 1) { if (re[0] + im[31] == 123.456f) out[0] = 1.f; continue; }
-          // |S|^2 -> dB of 32 bins (independent chains), one-sided doubling for all bins; the (at most two)
-          // un-doubled positions are corrected below
-          const uint32_t a_row = a_db + (uint32_t)((lane * TC_DBS + gi * 32) * 4);
+          // |S|^2 -> dB of 32 bins (independent chains, two bins per packed FMUL2 / FFMA2), one-sided doubling for
+          // all bins; the (at most two) un-doubled positions are corrected below
+          const uint32_t a_row = a_db + (uint32_t)((lane * DBS + gi * 32) * 4);
           const float2 kk = make_float2(K_DB, K_DB);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {                 // two bins per packed instruction (FMUL2 / FFMA2)
+          for (int j = 0; j < 32; j += 2) {
             const float2 r2 = make_float2(re[j], re[j + 1]), i2 = make_float2(im[j], im[j + 1]);
             const float2 p2 = fma2(r2, r2, mul2(i2, i2));
             const float2 l2 = make_float2(lg2_approx(p2.x), lg2_approx(p2.y));
@@ -361,45 +376,56 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           if ((sp0 >= p_lo && sp0 < p_lo + 32) || (sp1 >= p_lo && sp1 < p_lo + 32)) {
             __syncwarp();
             const int sp = (sp0 >= p_lo && sp0 < p_lo + 32) ? sp0 : sp1;
-            const uint32_t aa = a_db + (uint32_t)((lane * TC_DBS + (sp - pos_c0)) * 4);
+            const uint32_t aa = a_db + (uint32_t)((lane * DBS + (sp - pos_c0)) * 4);
             sts32(aa, lds32(aa) - K_DB);
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");        // the quarter's 128 dB values per column are complete
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(SW * 32) : "memory");   // the quarter's dB rows are complete
         // ---- interp1 onto the log-frequency axis: queries whose bracket lies in this chunk, in blocks of 32 ----
-        const int Qa = s_qrng[ch], Qb = s_qrng[ch + 1];
+        const int Qa = s_qrng[ch], Qb = (dbg_mode == 2) ? s_qrng[ch] : s_qrng[ch + 1];
         if (LAYOUT == 0) {
-          // lanes = 32 consecutive queries (coalesced 128-byte rows, no staging); the four warps of a quarter
-          // split its 32 columns, so the work is balanced whatever the number of query blocks
-          const int c_lo = sw * 8;
+          // lanes = 32 consecutive queries (coalesced 128-byte rows, no staging); the SW warps of a quarter split
+          // its 32 columns, so the work is balanced whatever the number of query blocks
+          const int c_lo = sw * CW;
           for (int b = Qa >> 5; b * 32 < Qb; ++b) {
             const int q = b * 32 + lane;
             const bool ok = q >= Qa && q < Qb;
             const int jl = ok ? __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0 : 0;
             const float a = lds32(a_aq + 4 * q);
-            const uint32_t ad = a_db + (uint32_t)((c_lo * TC_DBS + jl) * 4);
+            const uint32_t ad = a_db + (uint32_t)((c_lo * DBS + jl) * 4);
             if (NQC > 0 && ncols_valid == 32) {
               float* ptr = out_warp + (unsigned long long)c_lo * NQC + q;
-              float lo[8], hi[8];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) { lo[c] = lds32(ad + (uint32_t)(c * TC_DBS * 4)); hi[c] = lds32(ad + (uint32_t)(c * TC_DBS * 4 + 4)); }
-              if (ok) {
+              for (int c8 = 0; c8 < CW; c8 += 8) {
+                float lo[8], hi[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) ptr[c * NQC] = fmaf(a, hi[c] - lo[c], lo[c]);
+                for (int c = 0; c < 8; ++c) {
+                  lo[c] = lds32(ad + (uint32_t)((c8 + c) * DBS * 4));
+                  hi[c] = lds32(ad + (uint32_t)((c8 + c) * DBS * 4 + 4));
+                }
+                if (ok && dbg_mode != 3) {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) ptr[(c8 + c) * NQC] = fmaf(a, hi[c] - lo[c], lo[c]);
+                } else if (dbg_mode == 3) {
+                  float acc = 0.f;
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) acc += fmaf(a, hi[c] - lo[c], lo[c]);
+                  if (acc == 123.456f) ptr[0] = acc;
+                }
               }
             } else if (ok) {
               float* ptr = out_warp + (unsigned long long)c_lo * nq + q;
-              for (int c = 0; c < 8 && c_lo + c < ncols_valid; ++c) {
-                const float lo = lds32(ad + (uint32_t)(c * TC_DBS * 4)), hi = lds32(ad + (uint32_t)(c * TC_DBS * 4 + 4));
+              for (int c = 0; c < CW && c_lo + c < ncols_valid; ++c) {
+                const float lo = lds32(ad + (uint32_t)(c * DBS * 4)), hi = lds32(ad + (uint32_t)(c * DBS * 4 + 4));
                 ptr[(unsigned long long)c * nq] = fmaf(a, hi - lo, lo);
               }
             }
           }
         } else {
-          // lanes = columns: coalesced rows of the frequency-major layout; query blocks are dealt to the four warps
-          for (int b = (Qa >> 5) + ((sw - (Qa >> 5) - ch) & 3); b * 32 < Qb; b += 4) {
+          // lanes = columns: coalesced rows of the frequency-major layout; query blocks are dealt to the SW warps
+          for (int b = (Qa >> 5) + ((sw + SW * 64 - (Qa >> 5) % SW - ch % SW) % SW); b * 32 < Qb; b += SW) {
             const int q0 = max(Qa, b * 32), q1 = min(Qb, b * 32 + 32);
-            const uint32_t ad = a_db + (uint32_t)(lane * TC_DBS * 4);
+            const uint32_t ad = a_db + (uint32_t)(lane * DBS * 4);
             for (int q = q0; q < q1; ++q) {
               const int jq = __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0;
               const float a = lds32(a_aq + 4 * q);
@@ -408,18 +434,22 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
             }
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");        // dB rows may be overwritten by the next chunk
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(SW * 32) : "memory");   // dB rows may be overwritten by the next chunk
+      }
+      if (ABUF == 1 && next < n_tiles) {                  // single A buffer: rebuild once this tile's MMAs have retired
+        mbar_wait(BAR(2), (uint32_t)(it & 1));
+        build_a(next, 0);
       }
     }
-  } else if (warp == TC_EPI_WARPS) {
+  } else if (warp == EW) {
     // ===================== MMA issuer: one thread drives the tensor core =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
       unsigned long long it = 0;
       for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int abuf = (int)(it & 1);
-        mbar_wait(BAR(0 + abuf), (uint32_t)((it >> 1) & 1));
-        const uint32_t aA = smem_u32(sA) + (uint32_t)(abuf * 4 * TC_MAT_BYTES);
+        const int abuf = (ABUF == 2) ? (int)(it & 1) : 0;
+        mbar_wait(BAR(0 + abuf), (uint32_t)(((ABUF == 2) ? (it >> 1) : it) & 1));
+        const uint32_t aA = smem_u32(sA) + (uint32_t)(abuf * 4 * TC_A_MAT_BYTES);
         for (int ch = 0; ch < n_chunks; ++ch) {
           const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
           const int st = (int)(cseq & 1);
@@ -427,12 +457,12 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           mbar_wait(BAR(4 + st), par);               // B tile landed
           mbar_wait(BAR(10 + st), par ^ 1);          // TMEM stage drained (passes immediately the first two times)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t aB = smem_u32(sB) + (uint32_t)(st * TC_B_BYTES);
+          const uint32_t aB = smem_u32(sB) + (uint32_t)(st * S::B_BYTES);
 #pragma unroll
           for (int part = 0; part < 2; ++part) {          // 0: Re = E * C^T, 1: Im = O * S^T
-            const uint32_t d = tmem_base + (uint32_t)(st * 2 * TC_N + part * TC_N);
-            const uint32_t a_hi = aA + (uint32_t)((2 * part) * TC_MAT_BYTES), a_lo = a_hi + TC_MAT_BYTES;
-            const uint32_t b_hi = aB + (uint32_t)((2 * part) * TC_MAT_BYTES), b_lo = b_hi + TC_MAT_BYTES;
+            const uint32_t d = tmem_base + (uint32_t)(st * 2 * BN + part * BN);
+            const uint32_t a_hi = aA + (uint32_t)((2 * part) * TC_A_MAT_BYTES), a_lo = a_hi + TC_A_MAT_BYTES;
+            const uint32_t b_hi = aB + (uint32_t)((2 * part) * S::B_MAT_BYTES), b_lo = b_hi + S::B_MAT_BYTES;
 #pragma unroll
             for (int ks = 0; ks < TC_KP / 8; ++ks) {
               const uint32_t o = (uint32_t)(ks * 256);
@@ -457,8 +487,8 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
           const int st = (int)(cseq & 1);
           mbar_wait(BAR(6 + st), (uint32_t)(((cseq >> 1) & 1) ^ 1));
-          mbar_expect_tx(BAR(4 + st), TC_B_BYTES);
-          bulk_g2s(smem_u32(sB) + (uint32_t)(st * TC_B_BYTES), tcB + (size_t)ch * (TC_B_BYTES / 4), TC_B_BYTES, BAR(4 + st));
+          mbar_expect_tx(BAR(4 + st), S::B_BYTES);
+          bulk_g2s(smem_u32(sB) + (uint32_t)(st * S::B_BYTES), tcB + (size_t)ch * (S::B_BYTES / 4), S::B_BYTES, BAR(4 + st));
         }
       }
     }
@@ -466,48 +496,57 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == TC_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  if (warp == EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS));
+}
+
+static int tc_shape_bn() {
+  static int bn = 0;
+  if (!bn) { const char* v = getenv("FMCW_TC_BN"); bn = (v && atoi(v) == 64) ? 64 : 128; }
+  return bn;
 }
 
 size_t stft_tc_table_bytes(int nb_max) {
-  const int n_chunks = (nb_max - 1 + TC_STEP - 1) / TC_STEP + 1;
-  return (size_t)n_chunks * TC_B_BYTES;
+  // rows = chunks * BN; the BN = 64 shape has the most chunks
+  const size_t c64 = (size_t)((nb_max - 1 + 62) / 63 + 1) * 64, c128 = (size_t)((nb_max - 1 + 126) / 127 + 1) * 128;
+  return (c64 > c128 ? c64 : c128) * TC_KP * 4 * 4;
 }
-size_t stft_tc_meta_bytes(int nb_max) {
-  const int n_chunks = (nb_max - 1 + TC_STEP - 1) / TC_STEP + 1;
-  return (size_t)n_chunks * TC_N * sizeof(uint32_t);
+size_t stft_tc_meta_bytes(int) { return 16; }
+
+cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t*, int nb_max,
+                                   cudaStream_t st) {
+  const int bn = tc_shape_bn();
+  const int n_chunk_cap = (nb_max - 1 + bn - 2) / (bn - 1) + 1;
+  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, bn, n_chunk_cap);
+  return cudaGetLastError();
 }
 
-cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t* tc_meta, int nb_max,
-                                   cudaStream_t st) {
-  const int n_chunk_cap = (nb_max - 1 + TC_STEP - 1) / TC_STEP + 1;
-  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, tc_meta, n_chunk_cap);
+template <int L, int Q, class S>
+static cudaError_t launch_tc_shape(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
+                                   unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, cudaStream_t st,
+                                   const double* gmax_dev, int sms, int dbg) {
+  cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<L, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM);
+  if (e != cudaSuccess) return e;
+  stft_tc_kernel<L, Q, S><<<sms * S::CTAS, S::THREADS, S::SMEM, st>>>(t, g, x, out, tcB, capacity_cols, ld_cols, d_err, dbg, gmax_dev);
   return cudaGetLastError();
 }
 
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
-                                const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
+                                const uint32_t*, unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const size_t smem = TC_SMEM_BAR_OFF + 16 * 8 + 16;
   static int dbg = -1;
   if (dbg < 0) { const char* v = getenv("FMCW_TC_DEBUG"); dbg = v ? atoi(v) : 0; }
-  cudaError_t e = cudaSuccess;
-#define FMCW_TC_LAUNCH(L, Q)                                                                                       \
-  do {                                                                                                             \
-    e = cudaFuncSetAttribute(stft_tc_kernel<L, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    if (e != cudaSuccess) return e;                                                                                \
-    stft_tc_kernel<L, Q><<<sms, TC_THREADS, smem, st>>>(t, g, x, out, tcB, tc_meta, capacity_cols, ld_cols, d_err, dbg, gmax_dev); \
-  } while (0)
-  if (layout == 0) {
-    if (g.nq == 1024) FMCW_TC_LAUNCH(0, 1024);
-    else FMCW_TC_LAUNCH(0, 0);
-  } else {
-    FMCW_TC_LAUNCH(1, 0);
+  using S1 = TcShape<128, 16, 1>;
+  using S2 = TcShape<64, 8, 2>;
+#define FMCW_TC_ARGS t, g, x, out, tcB, capacity_cols, ld_cols, d_err, st, gmax_dev, sms, dbg
+  if (tc_shape_bn() == 128) {
+    if (layout != 0) return launch_tc_shape<1, 0, S1>(FMCW_TC_ARGS);
+    return g.nq == 1024 ? launch_tc_shape<0, 1024, S1>(FMCW_TC_ARGS) : launch_tc_shape<0, 0, S1>(FMCW_TC_ARGS);
   }
-#undef FMCW_TC_LAUNCH
-  return cudaGetLastError();
+  if (layout != 0) return launch_tc_shape<1, 0, S2>(FMCW_TC_ARGS);
+  return g.nq == 1024 ? launch_tc_shape<0, 1024, S2>(FMCW_TC_ARGS) : launch_tc_shape<0, 0, S2>(FMCW_TC_ARGS);
+#undef FMCW_TC_ARGS
 }
 
 }  // namespace fmcw
