@@ -133,7 +133,7 @@ struct fmcw_handle {
   // STFT tables
   StftTables st{};
   StftGeom geom{};
-  DevBuf plan, bins, kcb, qpos, aq, qend, coef, swin, hard, derr;
+  DevBuf plan, bins, kcb, wdc, qpos, aq, qend, coef, swin, hard, derr;
   // scratch
   DevBuf shard_geom, tcb, tcmeta, colub;
   DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, o_slow64, f32_stage, xc, det_list, ndet, inten, synth_tab;
@@ -189,7 +189,7 @@ fmcw_status validate(const fmcw_config* c, std::string& why) {
   if (c->num_ADC_samples_per_chirp < 1 || c->num_ADC_samples_per_chirp > 4096) { why = "num_ADC_samples_per_chirp out of [1,4096]"; return FMCW_ERR_CONFIG; }
   if (c->num_chirps_per_frame < 1 || c->num_chirps_per_frame > 4096) { why = "num_chirps_per_frame out of [1,4096]"; return FMCW_ERR_CONFIG; }
   if (c->num_Rx_antennas < 1 || c->rx_select >= c->num_Rx_antennas) { why = "rx_select out of range"; return FMCW_ERR_CONFIG; }
-  if (c->window_length < 2 || c->window_length > 1024) { why = "window_length out of [2,1024]"; return FMCW_ERR_CONFIG; }
+  if (c->window_length < 2 || c->window_length > 400) { why = "window_length out of [2,400]"; return FMCW_ERR_CONFIG; }
   if (c->overlap >= c->window_length) { why = "overlap must be < window_length (RP:179)"; return FMCW_ERR_CONFIG; }
   if (c->MAX_FREQ_BINS < 2 || c->MAX_FREQ_BINS > (uint32_t)MAX_NQ) { why = "MAX_FREQ_BINS out of [2,1024]"; return FMCW_ERR_CONFIG; }
   if (c->peak_mode > 1) { why = "peak_mode"; return FMCW_ERR_CONFIG; }
@@ -201,6 +201,7 @@ void fill_tables(fmcw_handle* h) {
   h->st.plan = h->plan.as<StftPlan>();
   h->st.bins = h->bins.as<int>();
   h->st.kcb = h->kcb.as<float>();
+  h->st.wdc = h->wdc.as<float>();
   h->st.qpos = h->qpos.as<int>();
   h->st.aq = h->aq.as<float>();
   h->st.qend = h->qend.as<int>();
@@ -477,6 +478,28 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
 
   h->geom.win = c.window_length; h->geom.hop = c.window_length - c.overlap; h->geom.nq = c.MAX_FREQ_BINS;
   h->geom.fs = 1.0 / c.PRT;
+  {
+    // rho = sup over [pi/(win-1), pi] of |W(w)|/W(0): grid maximum plus the Lipschitz slack of the grid spacing.
+    // With it, sup |S(w)| <= rho * sum(w x) + sum w |x - xbar| certifies most candidate columns in O(win).
+    const int win = (int)c.window_length;
+    double W0 = 0.0, Dw = 0.0;
+    const double c0 = 0.5 * (win - 1);
+    for (int n = 0; n < win; ++n) { W0 += wk[n]; Dw += std::fabs(n - c0) * wk[n]; }
+    double rho = 0.0;
+    if (win > 2) {
+      const int G = 64 * win;
+      const double w_lo = M_PI / (win - 1), delta = (M_PI - w_lo) / G;
+      for (int gi = 0; gi < G; ++gi) {
+        const double w = w_lo + (gi + 0.5) * delta;
+        double re = 0.0, im = 0.0;
+        for (int n = 0; n < win; ++n) { re += wk[n] * std::cos(w * (n - c0)); im += wk[n] * std::sin(w * (n - c0)); }
+        const double mag = std::sqrt(re * re + im * im);
+        rho = mag > rho ? mag : rho;
+      }
+      rho = (rho + Dw * delta * 0.5) / W0;
+    }
+    h->geom.rho = (float)(rho * (1.0 + 1e-6));
+  }
   const int nb_max = 2 * (int)c.MAX_FREQ_BINS + 2;
   const int half = (int)c.window_length / 2;
   cudaError_t e = cudaSuccess;
@@ -486,7 +509,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   ok(upload(h->tw_re, twre, h->stream)); ok(upload(h->tw_im, twim, h->stream));
   ok(upload(h->dop_tw, dtw, h->stream)); ok(upload(h->dop_win, dwin, h->stream));
   ok(upload(h->swin, swin, h->stream));
-  ok(h->plan.ensure(sizeof(StftPlan))); ok(h->bins.ensure((size_t)nb_max * 4)); ok(h->kcb.ensure((size_t)nb_max * 4));
+  ok(h->plan.ensure(sizeof(StftPlan))); ok(h->bins.ensure((size_t)nb_max * 4)); ok(h->kcb.ensure((size_t)nb_max * 4)); ok(h->wdc.ensure((size_t)nb_max * 4));
   ok(h->qpos.ensure(MAX_NQ * 4)); ok(h->aq.ensure(MAX_NQ * 4)); ok(h->qend.ensure((size_t)(nb_max + 2) * 4));
   ok(h->coef.ensure((size_t)nb_max * 2 * half * 4 + 64));
   h->st.hard_cap = 1u << 20;
@@ -510,7 +533,7 @@ void fmcw_destroy(fmcw_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb,
+  DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
                    &h->synth_tab, &h->shard_geom, &h->tcb, &h->tcmeta, &h->colub};

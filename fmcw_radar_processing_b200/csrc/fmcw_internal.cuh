@@ -74,6 +74,7 @@ struct StftTables {             // device arrays owned by the handle
   int* qend;                    // [nb_max+1] queries [qend[p-1], qend[p]) complete when position p is known
   float* coef;                  // [nb_max][2*half] cos((m+d)w), sin((m+d)w)
   float* win;                   // [win] kaiser window (host computed, float64 -> float32)
+  float* wdc;                   // [nb_max] window DC response per bin position (generic-window kernel)
   unsigned int* hard_list;      // columns whose max needs the exhaustive search
   unsigned int hard_cap;
   float* col_ub;                // [local columns] trivial upper bound 2*(sum|y|)^2 of each column's maximum
@@ -82,7 +83,11 @@ struct StftTables {             // device arrays owned by the handle
   int nb_max;
 };
 
-struct StftGeom { uint32_t win, hop, nq; double fs; };
+struct StftGeom {
+  uint32_t win, hop, nq;
+  double fs;
+  float rho;   // rigorous bound of max_{w >= pi/(win-1)} |W(w)| / W(0) of the STFT window (host, float64)
+};
 
 // sizes of a sharded run, resolved on the device from the all-gathered shard headers
 struct ShardGeom { unsigned long long L_total, sample_offset, L_local, L_avail; };

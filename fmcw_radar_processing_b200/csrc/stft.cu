@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
   const int half = win / 2;
   const int odd = win & 1;
   const long long mod = (long long)(2 * nfft);
-  // (the tensor-core path tabulates its own operands and only needs the rows of bins 0/1 here)
-  const int n_rows = (coef_rows > 0 && coef_rows < nb) ? coef_rows : nb;
+  // only the rows of bins 0/1 (stft_colstat_kernel) are tabulated here; the full table of the CUDA-core kernels
+  // comes from stft_coef_kernel, the tensor-core operands from stft_tc_prepare_kernel
+  const int n_rows = nb < 2 ? nb : 2;
   for (int i = tid; i < n_rows * half; i += blockDim.x) {
     const int p = i / half, m = i - p * half;
     const long long bin = t.bins[p];
@@ -184,6 +185,41 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
       if (p1 - P->chunk_p0[k] + 1 > NP_MAX) bad = 1;
     }
     if (bad) P->valid = -3;
+  }
+}
+
+// full coefficient table [nb][2*half] and the window DC response per bin for the CUDA-core kernels
+__global__ void __launch_bounds__(256) stft_coef_kernel(StftTables t, StftGeom g) {
+  const StftPlan* P = t.plan;
+  if (P->valid <= 0) return;
+  const int nb = P->nb, win = (int)g.win, half = win / 2, odd = win & 1;
+  const unsigned long long nfft = P->nfft;
+  const long long mod = (long long)(2 * nfft);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb * half; i += gridDim.x * blockDim.x) {
+    const int p = i / half, m = i - p * half;
+    const long long bin = t.bins[p];
+    const long long twod = odd ? (2 * m + 2) : (2 * m + 1);
+    const long long r = (twod * bin) % mod;
+    double sn, cs;
+    sincospi((double)r / (double)nfft, &sn, &cs);
+    t.coef[(size_t)p * 2 * half + m] = (float)cs;
+    t.coef[(size_t)p * 2 * half + half + m] = (float)sn;
+  }
+  // window DC response sum_n w[n] cos((n - c) w_p) (the window is symmetric, the sine part vanishes): the multiplier
+  // of the column mean in the generic kernel's DC split; one warp per bin position
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int p = gw; p < nb; p += nw) {
+    const long long bin = t.bins[p];
+    double acc = (odd && lane == 0) ? (double)t.win[half] : 0.0;
+    for (int m = lane; m < half; m += 32) {
+      const long long twod = odd ? (2 * m + 2) : (2 * m + 1);
+      const long long r = (twod * bin) % mod;
+      const int lo = half - 1 - m, hi = odd ? (half + 1 + m) : (half + m);
+      acc += ((double)t.win[lo] + (double)t.win[hi]) * cospi((double)r / (double)nfft);
+    }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
+    if (lane == 0) t.wdc[p] = (float)acc;
   }
 }
 
@@ -254,8 +290,11 @@ __global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (blockIdx.x == 0 && threadIdx.x == 0 && export_dst) *export_dst = 0.0; return; }
   __shared__ float s_w[1024];
+  __shared__ float s_wsum;
   const int win = (int)g.win;
   for (int i = threadIdx.x; i < win; i += blockDim.x) s_w[i] = t.win[i];
+  __syncthreads();
+  if (threadIdx.x == 0) { float a = 0.f; for (int i = 0; i < win; ++i) a += s_w[i]; s_wsum = a; }
   __syncthreads();
   const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
   const float lb = P->lb_max;
@@ -270,12 +309,22 @@ __global__ void __launch_bounds__(256) stft_refine_kernel(StftTables t, StftGeom
     if (col < ce && t.col_ub[col - cb] > lb) {         // only columns whose trivial bound beats the lower bound
       const sig_t* xs = x + (col * g.hop - off);
       const float c0 = 0.5f * (float)(win - 1);
+      float s0 = 0.f;
       for (int n = 0; n < win; ++n) {
         const float y = s_w[n] * (float)xs[n];
         nonneg = nonneg && (y >= 0.f);
+        s0 += y;
         dl = fmaf(fabsf((float)n - c0), fabsf(y), dl);
       }
       cand = true;
+      if (nonneg) {
+        // O(win) certificate: x = xbar + r gives sup_{w >= pi/(win-1)} |S(w)| <= rho * sum(w x) + sum w |x - xbar|
+        const float xbar = s0 / s_wsum;
+        float rs = 0.f;
+        for (int n = 0; n < win; ++n) rs = fmaf(s_w[n], fabsf((float)xs[n] - xbar), rs);
+        const float bnd = fmaf(g.rho, s0, rs);
+        if (2.f * bnd * bnd * 1.00002f <= lb) { cand = false; atomicAdd(&P->n_refined, 1u); }
+      }
     }
     unsigned mask = __ballot_sync(0xffffffffu, cand);
     while (mask) {
@@ -557,53 +606,99 @@ stft_main_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* _
   }
 }
 
-// Generic window length (any win >= 2, any hop): one thread per column, taps staged in shared memory.
-// Correct for every configuration; the specialised kernel above is the fast path for the reference's
-// window_length = 20.
+// Generic window length (any win >= 2, any hop, odd lengths): one thread per column, the folded taps of the 128
+// columns of a CTA in shared memory (thread-minor), bins in register tiles of 8 whose coefficients are staged
+// as [tap][cos x 8 | sin x 8] (four broadcast LDS.128 per tap -> 16 FMAs).  The column mean is removed in float64
+// and re-enters through the tabulated window response (same DC split as the tensor-core kernel).  Time-major
+// output is staged per warp like in stft_main_kernel.  This is the path of the C5 window / hop sweep.
 template <int LAYOUT>
 __global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x,
                                                            float* __restrict__ out, unsigned long long capacity_cols,
                                                            unsigned long long ld_cols, int* d_err) {
   const StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
-  extern __shared__ float s_dyn[];   // [2*half + odd][128] even / odd parts (+ centre), thread-minor
+  constexpr int QF = 16, BT = 8;
+  extern __shared__ __align__(16) float s_dyn[];
   const int win = (int)g.win, half = win / 2, odd = win & 1;
-  const int tid = threadIdx.x;
+  float* s_eo = s_dyn;                                   // [2*half][128] even / odd parts, thread-minor
+  float* s_cf = s_eo + (size_t)2 * half * 128;           // [half][16] coefficient tile: cos of 8 bins | sin of 8 bins
+  float* s_stage = s_cf + (size_t)half * 16;             // [4 warps][32][QF+1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
   const unsigned long long ncl = ce - cb;
   if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
   const int nq = P->nq, nb = P->nb;
   const float inv = (float)(1.0 / sqrt(P->pmax_raw));
   const unsigned long long n_blk = (ncl + 127) / 128;
+  const uint32_t a_stage = smem_u32(s_stage) + (uint32_t)(warp * 32 * (QF + 1) * 4);
+  const uint32_t a_st_lane = a_stage + (uint32_t)(lane * (QF + 1) * 4);
   for (unsigned long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
     unsigned long long col = cb + blk * 128 + tid;
     const bool act = col < ce;
     if (!act) col = ce - 1;
     const sig_t* xs = x + (col * g.hop - off);
+    double mean_d = 0.0;
+    for (int n = 0; n < win; ++n) mean_d += xs[n];
+    mean_d /= (double)win;
+    const float mean = (float)mean_d;
     for (int m = 0; m < half; ++m) {
-      const int lo = odd ? (half - 1 - m) : (half - 1 - m), hi = odd ? (half + 1 + m) : (half + m);
-      const float ylo = t.win[lo] * inv * (float)xs[lo], yhi = t.win[hi] * inv * (float)xs[hi];
-      s_dyn[m * 128 + tid] = ylo + yhi;
-      s_dyn[(half + m) * 128 + tid] = ylo - yhi;
+      const int lo = half - 1 - m, hi = odd ? (half + 1 + m) : (half + m);
+      const float ylo = t.win[lo] * inv * (float)(xs[lo] - (double)mean), yhi = t.win[hi] * inv * (float)(xs[hi] - (double)mean);
+      s_eo[m * 128 + tid] = ylo + yhi;
+      s_eo[(half + m) * 128 + tid] = ylo - yhi;
     }
-    const float yc = odd ? t.win[half] * inv * (float)xs[half] : 0.f;
+    const float yc = odd ? t.win[half] * inv * (float)(xs[half] - (double)mean) : 0.f;
+    const float xb = mean * inv;
+    const unsigned long long warp_col0 = cb + blk * 128 + (unsigned long long)warp * 32;
+    const int ncols_valid = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 32ull ? (ce - warp_col0) : 32ull);
+    float* out_warp = out + (warp_col0 - cb) * (unsigned long long)nq;
     float prev = 0.f;
-    for (int p = 0; p < nb; ++p) {
-      const float* cf = t.coef + (size_t)p * 2 * half;
-      float re = yc, im = 0.f;
-      for (int m = 0; m < half; ++m) {
-        re = fmaf(s_dyn[m * 128 + tid], __ldg(cf + m), re);
-        im = fmaf(s_dyn[(half + m) * 128 + tid], __ldg(cf + half + m), im);
+    int qcur = 0;
+    for (int pb = 0; pb < nb; pb += BT) {
+      __syncthreads();                                   // previous coefficient tile consumed
+      for (int i = tid; i < half * 16; i += 128) {
+        const int m = i >> 4, j = i & 15, p = pb + (j & 7);
+        s_cf[i] = (p < nb) ? t.coef[(size_t)p * 2 * half + ((j < 8) ? m : half + m)] : 0.f;
       }
-      const float db = fmaf(K_DB, __log2f(fmaf(re, re, im * im)), t.kcb[p]);
-      if (p > 0 && act) {
-        for (int q = t.qend[p - 1]; q < t.qend[p]; ++q) {
-          const float v = fmaf(t.aq[q], db - prev, prev);
-          if (LAYOUT == 0) out[(col - cb) * (unsigned long long)nq + q] = v;
-          else out[(unsigned long long)q * ld_cols + (col - cb)] = v;
+      __syncthreads();
+      float re[BT], im[BT];
+#pragma unroll
+      for (int j = 0; j < BT; ++j) { re[j] = yc; im[j] = 0.f; }
+      for (int m = 0; m < half; ++m) {
+        const float e = s_eo[m * 128 + tid], o = s_eo[(half + m) * 128 + tid];
+        const float4 c0 = *reinterpret_cast<const float4*>(s_cf + m * 16), c1 = *reinterpret_cast<const float4*>(s_cf + m * 16 + 4);
+        const float4 s0 = *reinterpret_cast<const float4*>(s_cf + m * 16 + 8), s1 = *reinterpret_cast<const float4*>(s_cf + m * 16 + 12);
+        re[0] = fmaf(e, c0.x, re[0]); re[1] = fmaf(e, c0.y, re[1]); re[2] = fmaf(e, c0.z, re[2]); re[3] = fmaf(e, c0.w, re[3]);
+        re[4] = fmaf(e, c1.x, re[4]); re[5] = fmaf(e, c1.y, re[5]); re[6] = fmaf(e, c1.z, re[6]); re[7] = fmaf(e, c1.w, re[7]);
+        im[0] = fmaf(o, s0.x, im[0]); im[1] = fmaf(o, s0.y, im[1]); im[2] = fmaf(o, s0.z, im[2]); im[3] = fmaf(o, s0.w, im[3]);
+        im[4] = fmaf(o, s1.x, im[4]); im[5] = fmaf(o, s1.y, im[5]); im[6] = fmaf(o, s1.z, im[6]); im[7] = fmaf(o, s1.w, im[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < BT; ++j) {
+        const int p = pb + j;
+        if (p < nb) {
+          const float r = fmaf(xb, __ldg(t.wdc + p), re[j]);          // + mean * window DC response
+          const float db = fmaf(K_DB, lg2_approx(fmaf(r, r, im[j] * im[j])), __ldg(t.kcb + p));
+          if (p > 0) {
+            const int qe = __ldg(t.qend + p);
+            for (; qcur < qe; ++qcur) {
+              const float v = fmaf(__ldg(t.aq + qcur), db - prev, prev);
+              if (LAYOUT == 0) {
+                const int slot = qcur & (QF - 1);
+                sts32(a_st_lane + (uint32_t)(slot * 4), v);
+                if (slot == QF - 1) flush_stage<QF, 32>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - (QF - 1), QF, lane);
+              } else if (act) {
+                out[(unsigned long long)qcur * ld_cols + (col - cb)] = v;
+              }
+            }
+          }
+          prev = db;
         }
       }
-      prev = db;
+    }
+    if (LAYOUT == 0) {
+      const int rem = qcur & (QF - 1);
+      if (rem) flush_stage<QF, 32>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - rem, rem, lane);
     }
   }
 }
@@ -654,7 +749,8 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
   const bool tc = (g.win == 20 && stft_variant() < 0);
   stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks,
                                        tc ? 2 : 0, gathered, world, rank, xc);
-  if (tc) return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st);
+  if (!tc) { stft_coef_kernel<<<128, 256, 0, st>>>(t, g); return cudaGetLastError(); }
+  return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st);
   return cudaGetLastError();
 }
 
@@ -710,7 +806,7 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t
       case 0: return launch_main_variant<10, 2, 16, 256, 3>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
     }
   } else {
-    const size_t smem = (size_t)(2 * (g.win / 2)) * 128 * sizeof(float);
+    const size_t smem = ((size_t)(2 * (g.win / 2)) * 128 + (size_t)(g.win / 2) * 16 + 4 * 32 * 17) * sizeof(float);
     cudaError_t e;
     if (layout == 0) {
       e = cudaFuncSetAttribute(stft_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

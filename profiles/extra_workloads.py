@@ -48,7 +48,7 @@ for name, n, n_rx, PN, NTS, win, ov, scene in CASES:
     tm = h.timings()
     info = h.info()
     bytes_alg = n * (NTS * PN * 4 + 256 * 4 + 16 + 64 + PN * 4) + info["L_total"] * 8 + info["ncol_local"] * 1024 * 4
-    print(f"{name:55s} {n / ms * 1e3:12.0f} {ms:9.3f} {tm['chain_ms']:8.3f} {tm['stft_main_ms']:8.3f} {bytes_alg / ms / 1e6:12.0f}"
+    print(f"{name:55s} {n / ms * 1e3:12.0f} {ms:9.3f} {tm["chain_ms"]:8.3f} {tm["stft_main_ms"]:8.3f} pm {tm["plan_max_ms"]:6.3f} {bytes_alg / ms / 1e6:12.0f}"
           f"   det {info['n_detected']} cols {info['ncol_local']} nfft 2^{int(np.log2(info['nfft']))} bins {info['n_dtft_bins']}")
     h.close()
     del iq, out, inten
