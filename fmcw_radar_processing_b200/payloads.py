@@ -60,16 +60,46 @@ def write_value(f: io.TextIOBase, v):
         f.write("]")
 
 
+NATIVE_MIN_ELEMS = 1 << 16      # larger float matrices go through the native multi-threaded writer
+
+
+def _native_append(path: str, a: np.ndarray) -> bool:
+    """Appends jsonencode(a) with libfmcw_cuda's host-side writer (no GPU involved); False if unavailable."""
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:
+        return False
+    if a.dtype not in (np.float32, np.float64) or a.ndim != 2:
+        return False
+    fn = lib.fmcw_json_append_f32 if a.dtype == np.float32 else lib.fmcw_json_append_f64
+    es = a.itemsize
+    if a.strides[0] % es or a.strides[1] % es:
+        return False
+    return fn(path.encode(), a.ctypes.data, a.shape[0], a.shape[1], a.strides[0] // es, a.strides[1] // es, 1) == 0
+
+
 def write_struct(path: str, fields) -> None:
-    """jsonencode(struct) with ``fields`` an ordered list of (name, value)."""
-    with open(path, "w") as f:
+    """jsonencode(struct) with ``fields`` an ordered list of (name, value).  Large float matrices (the spectrogram,
+    the range-FFT heat map) are streamed by the native writer, everything else by Python."""
+    f = open(path, "w")
+    try:
         f.write("{")
         for i, (k, v) in enumerate(fields):
             if i:
                 f.write(",")
             f.write(json.dumps(k) + ":")
+            a = v if isinstance(v, np.ndarray) else None
+            if a is not None and a.ndim == 2 and a.size >= NATIVE_MIN_ELEMS and 1 not in a.shape:
+                f.close()
+                ok = _native_append(path, a)
+                f = open(path, "a")
+                if ok:
+                    continue
             write_value(f, v)
         f.write("}")
+    finally:
+        f.close()
 
 
 def matlab_growing_matrix(values: np.ndarray, detected: np.ndarray) -> np.ndarray:

@@ -189,6 +189,15 @@ FMCW_API fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, ui
 FMCW_API fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,
                                          uint64_t frame, uint32_t chirp, float* out);
 
+/* Host-only helpers for the reference's JSON payloads (RP:307-318, 358-367, 386-396, 576-587): append the jsonencode
+ * text of a numeric matrix (element (r,c) at a[r*row_stride + c*col_stride], strides in elements) to a file.  Nested
+ * row-major like jsonencode, NaN/Inf -> null, shortest round-trip digits; flatten_vectors != 0 writes 1 x N and
+ * N x 1 matrices as flat arrays.  Rows are formatted by all host threads. */
+FMCW_API fmcw_status fmcw_json_append_f32(const char* path, const float* a, uint64_t rows, uint64_t cols,
+                                          int64_t row_stride, int64_t col_stride, int flatten_vectors);
+FMCW_API fmcw_status fmcw_json_append_f64(const char* path, const double* a, uint64_t rows, uint64_t cols,
+                                          int64_t row_stride, int64_t col_stride, int flatten_vectors);
+
 /* Synthetic scene generator: same bits as fmcw_radar_processing_b200/synth.py.
  * tables: float64 [n_frames][n_scat][4] (A, cycles/sample, cycles/chirp, phase cycles), host or device.
  * iq_out: device or host int16 [n_frames][n_rx][PN][NTS][2]. */

@@ -98,3 +98,31 @@ def test_main_reports_processing_failure_without_gpu(tmp_path):
     r = main({"processAnimalActivity": "no", "workdir": str(tmp_path)})
     assert r["status"] == "error" and r["message"] == "Failed at radar processing step."
     assert [s["step"] for s in r["steps"]] == ["Read Files", "Radar Processing"]
+
+
+def test_native_json_writer_matches_python_writer(tmp_path):
+    """fmcw_json_append_f32/f64 (host-only, multi-threaded) against the Python writer: same nesting, nulls, values."""
+    rng = np.random.default_rng(3)
+    a = (rng.standard_normal((300, 257)) * 40).astype(np.float32)
+    a[2, 3] = np.nan
+    a[5, 7] = np.inf
+    view = np.ascontiguousarray(a.T).T                      # strided like intensity[:ncol].T
+    d = rng.standard_normal((260, 256))
+    fields = [("time", np.arange(5) * 0.15), ("intensity", view), ("m64", d), ("title", "x")]
+    p_native, p_py = str(tmp_path / "n.json"), str(tmp_path / "p.json")
+    old = P.NATIVE_MIN_ELEMS
+    try:
+        P.NATIVE_MIN_ELEMS = 1
+        P.write_struct(p_native, fields)
+        P.NATIVE_MIN_ELEMS = 1 << 60
+        P.write_struct(p_py, fields)
+    finally:
+        P.NATIVE_MIN_ELEMS = old
+    n, p = json.load(open(p_native)), json.load(open(p_py))
+    assert list(n) == list(p) == ["time", "intensity", "m64", "title"]
+    assert n["intensity"][2][3] is None and n["intensity"][5][7] is None
+    gn = np.array([[np.nan if v is None else v for v in r] for r in n["intensity"]], dtype=np.float32)
+    m = np.isfinite(a)
+    assert np.array_equal(gn[m], a[m])                      # shortest round-trip digits reproduce every float32
+    assert np.allclose(np.array(n["m64"]), d, rtol=0, atol=0)
+    assert np.allclose(np.array(p["m64"]), d, rtol=1e-14)   # the Python writer prints 15 significant digits
