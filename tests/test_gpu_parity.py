@@ -217,3 +217,66 @@ def test_fleet_window_hop_sweep(api, win, overlap_pct):
         T, F, _, _ = h.stft_axes(info["L_total"])
         assert np.allclose(T, st["T"], rtol=1e-14) and np.allclose(F, st["frequency"], rtol=1e-14)
         h.close()
+
+
+def test_empty_and_single_frame_inputs(api):
+    from fmcw_radar_processing_b200 import FmcwError
+    case = H.make_case(n_frames=2, NTS=128, PN=64)
+    h = api(case["cfg"], case["calib"])
+    out = h.process_frames(case["iq"][:0])                    # no frames: nothing to do, no error
+    assert out["detected"].shape == (0,) and h.info()["n_detected"] == 0
+    with pytest.raises(FmcwError) as ei:                      # an empty slow-time signal has no spectrogram (RP:276)
+        h.run(case["iq"][:0])
+    assert ei.value.status == 8
+    ref = H.oracle_no(dict(case, iq=case["iq"][:1]))
+    out, inten = h.run(np.ascontiguousarray(case["iq"][:1]))  # one frame: 64 samples -> 45 columns, nfft = 64
+    info = h.info()
+    assert info["ncol_local"] == 45 and info["nfft"] == 64 == ref["stft"]["nfft"]
+    e_db, _ = H.spectrogram_errors(inten[:45].T, ref["stft"]["intensity"])
+    assert e_db < TOL_DB
+    h.close()
+
+
+def test_optional_outputs_may_be_null(api):
+    import ctypes as C
+    from fmcw_radar_processing_b200 import _lib
+    case = H.make_case(n_frames=6, NTS=64, PN=16)
+    h = api(case["cfg"], case["calib"])
+    full = h.process_frames(case["iq"])
+    only = {"range_bin": np.full(6, -7, np.int32)}            # every other per-frame output NULL
+    h.process_frames(case["iq"], only)
+    assert np.array_equal(only["range_bin"], full["range_bin"])
+    fo = _lib.fmcw_frame_out()                                # all NULL is legal too
+    st = h.lib.fmcw_process_frames(h._h, case["iq"].ctypes.data, 6, C.byref(fo))
+    assert st == 0 and h.info()["n_detected"] == int(full["detected"].sum())
+    h.close()
+
+
+def test_handle_is_not_reentrant(api):
+    """A second call while one is in flight returns FMCW_ERR_BUSY (include/fmcw_cuda.h, threading contract)."""
+    import threading
+    from fmcw_radar_processing_b200 import FmcwError
+    case = H.make_case(n_frames=400, NTS=128, PN=64)
+    h = api(case["cfg"], case["calib"])
+    seen = []
+
+    def worker():
+        for _ in range(6):
+            try:
+                h.run(case["iq"])
+                seen.append(0)
+            except FmcwError as e:
+                seen.append(e.status)
+
+    th = [threading.Thread(target=worker) for _ in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert set(seen) <= {0, 6} and 0 in seen                  # only OK or BUSY, never corruption
+    out, inten = h.run(case["iq"])
+    ref = H.oracle_no(case)
+    nc = h.info()["ncol_local"]
+    e_db, _ = H.spectrogram_errors(inten[:nc].T, ref["stft"]["intensity"])
+    assert e_db < TOL_DB
+    h.close()
