@@ -2,6 +2,7 @@
 //
 //   out = fmcw_cuda_mex('run', iq, calib_data, cfg)          % replaces RP:197-261 + RP:265-299
 //   out = fmcw_cuda_mex('frames', iq, calib_data, cfg)       % RP:197-261 only ('yes' branch, RP:457-530)
+//   out = fmcw_cuda_mex('stft_frames', [], calib_data, cfg)   % RP:538-566 on the signal of the last 'frames' call (float64 inside)
 //   out = fmcw_cuda_mex('stft', x, calib_data, cfg)          % RP:270-299 / RP:538-566 on a given signal
 //
 // iq    int16 [2 x NTS x PN x RX x N]  (MATLAB column-major == C [frame][rx][chirp][sample][I,Q])
@@ -85,14 +86,24 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     }
     const uint32_t NTS = c.num_ADC_samples_per_chirp, PN = c.num_chirps_per_frame, ND = c.Doppler_fft_size, NQ = c.MAX_FREQ_BINS;
     const bool is_stft = std::strcmp(cmd, "stft") == 0, is_run = std::strcmp(cmd, "run") == 0;
-    if (!is_stft && !is_run && std::strcmp(cmd, "frames") != 0) { err_id = "fmcw:usage"; err_msg = "cmd must be 'run', 'frames' or 'stft'"; break; }
+    const bool is_stft_frames = std::strcmp(cmd, "stft_frames") == 0;
+    if (!is_stft && !is_run && !is_stft_frames && std::strcmp(cmd, "frames") != 0) { err_id = "fmcw:usage"; err_msg = "cmd must be 'run', 'frames', 'stft_frames' or 'stft'"; break; }
     const char* names[] = {"detected", "range_idx", "range_mag", "doppler_idx", "range_max_abs", "doppler_row", "slow_time_mag",
                            "T", "frequency", "intensity", "nfft", "pmax"};
     plhs[0] = mxCreateStructMatrix(1, 1, 12, names);
     uint64_t L = 0, n = 0;
     fmcw_status st = FMCW_OK;
     mxArray* inten = nullptr;
-    if (is_stft) {
+    if (is_stft_frames) {
+      fmcw_run_info fi;
+      st = fmcw_get_info(g_handle, &fi);
+      if (st != FMCW_OK) { err_id = "fmcw:info"; err_msg = fmcw_last_error(g_handle); break; }
+      L = fi.L_local;
+      const uint64_t cap = L > c.overlap ? (L - c.overlap) / (c.window_length - c.overlap) : 1;
+      inten = mxCreateNumericMatrix(NQ, cap ? cap : 1, mxSINGLE_CLASS, mxREAL);
+      fmcw_stft_out so = {(float*)mxGetData(inten), cap ? cap : 1, 0, FMCW_LAYOUT_TIME_MAJOR, 0};
+      st = fmcw_stft_frames(g_handle, &so);
+    } else if (is_stft) {
       if (!mxIsSingle(prhs[1])) { err_id = "fmcw:type"; err_msg = "stft input must be single"; break; }
       L = (uint64_t)mxGetNumberOfElements(prhs[1]);
       const uint64_t cap = L > c.overlap ? (L - c.overlap) / (c.window_length - c.overlap) : 1;
