@@ -1,7 +1,8 @@
-"""Development probe (not a test): prints parity metrics of the CUDA path against the oracle."""
+"""Precision probe (not a test): prints parity metrics of the CUDA path against the float64 oracle, including the
+spectrogram error by level band quoted in DESIGN.md.  python profiles/precision_probe.py > profiles/precision_<round>.txt"""
 import sys, time
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from tests import helpers as H
 from oracle import fmcw_oracle as O
 from fmcw_radar_processing_b200.api import FmcwCuda
