@@ -102,7 +102,8 @@ def test_fused_run_spectrogram_parity(api, NTS, PN, nf):
     h.close()
 
 
-@pytest.mark.parametrize("L,win,ov", [(700, 20, 19), (5000, 20, 19), (40, 20, 19), (20, 20, 19), (3000, 32, 16),
+@pytest.mark.parametrize("L,win,ov", [(700, 20, 19), (5000, 20, 19), (40, 20, 19), (20, 20, 19), (3000, 20, 10), (4001, 20, 15),
+                                     (3000, 20, 0), (3000, 32, 16),
                                      (4000, 64, 48), (6000, 128, 115), (5000, 256, 128), (900, 21, 14), (1200, 33, 30)])
 def test_stft_isolated_parity(api, L, win, ov):
     """fmcw_stft on a given float32 sequence against the oracle on the same float32 values."""
