@@ -13,6 +13,7 @@ STATUS_NAMES = {0: "FMCW_OK", 1: "FMCW_ERR_CONFIG", 2: "FMCW_ERR_POINTER", 3: "F
                 5: "FMCW_ERR_OOM", 6: "FMCW_ERR_BUSY", 7: "FMCW_ERR_SIZE", 8: "FMCW_ERR_NO_DATA", 9: "FMCW_ERR_STATE"}
 PEAK_STRONGEST, PEAK_FIRST = 0, 1
 LAYOUT_TIME_MAJOR, LAYOUT_FREQ_MAJOR = 0, 1
+OPT_ASYNC_HOST = 1
 
 
 class FmcwError(RuntimeError):
@@ -56,6 +57,7 @@ EXPORTS = {
     "fmcw_last_error": (C.c_char_p, [C.c_void_p]),
     "fmcw_get_stream": (C.c_void_p, [C.c_void_p]),
     "fmcw_synchronize": (C.c_int, [C.c_void_p]),
+    "fmcw_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "fmcw_get_info": (C.c_int, [C.c_void_p, C.POINTER(fmcw_run_info)]),
     "fmcw_get_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4)]),
     "fmcw_process_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(fmcw_frame_out)]),

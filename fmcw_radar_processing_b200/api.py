@@ -77,6 +77,9 @@ class FmcwCuda:
     def synchronize(self):
         self._check(self.lib.fmcw_synchronize(self._h))
 
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.fmcw_set_option(self._h, option, value))
+
     def info(self) -> dict:
         inf = _lib.fmcw_run_info()
         self._check(self.lib.fmcw_get_info(self._h, C.byref(inf)))

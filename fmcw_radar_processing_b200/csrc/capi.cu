@@ -144,6 +144,7 @@ struct fmcw_handle {
   uint64_t plan_L = 0, plan_off = 0, plan_avail = 0;
   StftPlan plan_host{};
   int n_chunks = 12;
+  bool async_host = false;   // FMCW_OPT_ASYNC_HOST: calls with (pinned) host buffers return after enqueueing
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, chain, compact, plan+max, main
   bool ev_valid[5] = {false, false, false, false, false};
 };
@@ -352,6 +353,17 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
      "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
+  if (!dev_out && h->async_host) {
+    // no host round trip: copy the upper bound of the column count (columns past the real count are unspecified)
+    if (cap) {
+      if (sout->layout == FMCW_LAYOUT_TIME_MAJOR)
+        CK(cudaMemcpyAsync(sout->intensity, d_out, (size_t)cap * nq * 4, cudaMemcpyDeviceToHost, h->stream), "D2H intensity");
+      else
+        CK(cudaMemcpy2DAsync(sout->intensity, ld * 4, d_out, d_ld * 4, cap * 4, nq, cudaMemcpyDeviceToHost, h->stream),
+           "D2H intensity");
+    }
+    return FMCW_OK;
+  }
   if (!dev_out) {
     fmcw_status s = read_info(h);
     if (s != FMCW_OK) return s;
@@ -599,8 +611,18 @@ fmcw_status fmcw_process_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_fr
   if (s != FMCW_OK) return s;
   s = copy_frame_outputs(h, n_frames, out, d);
   if (s != FMCW_OK) return s;
-  if (any_host) CK(cudaStreamSynchronize(h->stream), "synchronize");
+  if (any_host && !h->async_host) CK(cudaStreamSynchronize(h->stream), "synchronize");
   return FMCW_OK;
+}
+
+fmcw_status fmcw_set_option(fmcw_handle* h, int option, int64_t value) {
+  if (!h) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  switch (option) {
+    case FMCW_OPT_ASYNC_HOST: h->async_host = value != 0; return FMCW_OK;
+    default: return fail(h, FMCW_ERR_CONFIG, "unknown option");
+  }
 }
 
 fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const fmcw_frame_out* fout,
@@ -619,7 +641,7 @@ fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const
   const uint64_t cols_up = L_up >= h->cfg.window_length ? (L_up - h->cfg.overlap) / h->geom.hop : 0;
   s = run_stft(h, true, 0, 0, 0, 0, true, 0.0, sout, cols_up);
   if (s != FMCW_OK) return s;
-  if (any_host) {
+  if (any_host && !h->async_host) {
     CK(cudaStreamSynchronize(h->stream), "synchronize");
     if (!h->have_info) { s = read_info(h); if (s != FMCW_OK) return s; }
     if (h->plan_host.valid == 0) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length slow-time samples");

@@ -135,6 +135,13 @@ FMCW_API void        fmcw_destroy(fmcw_handle* h);
 FMCW_API const char* fmcw_last_error(const fmcw_handle* h);
 FMCW_API void*       fmcw_get_stream(fmcw_handle* h);      /* cudaStream_t all work is queued on */
 FMCW_API fmcw_status fmcw_synchronize(fmcw_handle* h);
+
+/* Options.  FMCW_OPT_ASYNC_HOST = 1: fmcw_process_frames / fmcw_run with (pinned) host buffers return as soon as the
+ * copies and kernels are queued, so that two handles can overlap one recording's D2H with the next one's H2D; the
+ * intensity copy then covers the upper bound of the column count and the results are valid after fmcw_synchronize
+ * (sizes from fmcw_get_info). */
+enum { FMCW_OPT_ASYNC_HOST = 1 };
+FMCW_API fmcw_status fmcw_set_option(fmcw_handle* h, int option, int64_t value);
 FMCW_API fmcw_status fmcw_get_info(fmcw_handle* h, fmcw_run_info* info);   /* synchronises */
 
 /* Device time in ms of the stages of the last fmcw_run / fmcw_process_frames (CUDA events on the
