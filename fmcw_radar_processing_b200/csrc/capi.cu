@@ -125,6 +125,9 @@ struct fmcw_handle {
   fmcw_config cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;            // look-ahead STFT plan, concurrent with the frame chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool lookahead = false;
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   std::string err;
   // chain tables
@@ -341,9 +344,12 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
     cap = need; d_ld = need;
   }
   if (!h->planned) {
+    const int spec_mode = (from_device_count && h->lookahead) ? 2 : 0;
+    if (spec_mode) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0), "join look-ahead plan");
     CK(launch_stft_plan(h->st, h->geom, from_device_count ? h->ndet.as<unsigned long long>() : nullptr,
-                        h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks, h->stream),
-       "stft plan kernel");
+                        h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks, h->stream,
+                        nullptr, 0, 0, nullptr, spec_mode), "stft plan kernel");
+    h->lookahead = false;
     h->planned = true; h->plan_L = L_total; h->plan_off = offset; h->plan_avail = L_avail;
     if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream), "stft max kernels");
   }
@@ -426,6 +432,9 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FMCW_ERR_CUDA);
   for (cudaEvent_t& e : h->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(FMCW_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return bail(FMCW_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(FMCW_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return bail(FMCW_ERR_CUDA);
 
   // ---- calibration (RP:167-174), window (RP:138) and scale (RP:121, 203) folded into one table ----
   std::vector<std::complex<double>> cal(NTS, {0.0, 0.0});
@@ -551,6 +560,9 @@ void fmcw_destroy(fmcw_handle* h) {
                    &h->synth_tab, &h->shard_geom, &h->tcb, &h->tcmeta, &h->colub};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -633,6 +645,17 @@ fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const
   cudaSetDevice(h->device);
   FrameDev d{};
   bool any_host = false;
+  const uint64_t L_spec = n_frames * h->cfg.num_chirps_per_frame;
+  if (L_spec >= h->cfg.window_length) {
+    // look-ahead: plan the STFT for "every frame detects a target" on a side stream while the frame chain runs;
+    // the real plan launch confirms it on the device (or plans again if the detection count differs)
+    CK(cudaEventRecord(h->ev_fork, h->stream), "event");
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "fork look-ahead plan");
+    CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, L_spec, 0, L_spec, L_spec, h->n_chunks, h->side,
+                        nullptr, 0, 0, nullptr, 1), "look-ahead stft plan");
+    CK(cudaEventRecord(h->ev_join, h->side), "event");
+    h->lookahead = true;
+  }
   fmcw_status s = run_frames(h, iq, n_frames, fout, d, any_host);
   if (s != FMCW_OK) return s;
   s = copy_frame_outputs(h, n_frames, fout, d);

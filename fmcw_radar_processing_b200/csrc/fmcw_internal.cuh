@@ -58,7 +58,8 @@ cudaError_t launch_compact(const CompactParams& p, cudaStream_t st);
 struct StftPlan {
   unsigned long long L_total, nfft, ncol_total, col_begin, col_end, sample_offset, L_avail;
   int log2nfft, nb, nq, n_chunks, valid;
-  unsigned int n_hard, n_refined, task_counter, ticket_r, ticket_h, pad0;
+  unsigned int n_hard, n_refined, task_counter, ticket_r, ticket_h;
+  int spec_state;               // 1: planned ahead for the length in L_total (not yet confirmed), 2: confirmed, 0: none
   float lb_max;                 // max_t max(S0^2, 2|S(w1)|^2) (lower bound of the global max)
   double pmax_raw;              // final global max of c_j |S|^2
   int chunk_q0[MAX_CHUNKS + 1]; // query range of each chunk (multiples of 32 except the last end)
@@ -100,7 +101,7 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
                              cudaStream_t st, const double* gathered = nullptr, uint32_t world = 0, uint32_t rank = 0,
-                             sig_t* xc = nullptr);
+                             sig_t* xc = nullptr, int spec_mode = 0);
 cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const sig_t* x, cudaStream_t st,
                             double* export_dst = nullptr);
 cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
@@ -112,7 +113,7 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t
 size_t stft_tc_table_bytes(int nb_max);
 size_t stft_tc_meta_bytes(int nb_max);
 cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t* tc_meta, int nb_max,
-                                   cudaStream_t st);
+                                   cudaStream_t st, int spec_mode = 0);
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
                                 const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev = nullptr);

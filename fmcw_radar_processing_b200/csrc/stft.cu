@@ -23,12 +23,23 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          unsigned long long sample_offset,
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
                                                          int n_chunks_req, int coef_rows, const double* __restrict__ gathered,
-                                                         uint32_t world, uint32_t rank, sig_t* __restrict__ xc) {
+                                                         uint32_t world, uint32_t rank, sig_t* __restrict__ xc, int spec_mode) {
   __shared__ int s_scan[1024];
   __shared__ int s_wsum[32];
   __shared__ unsigned long long s_nfft;
   __shared__ int s_valid;
+  __shared__ int s_hit;
   StftPlan* P = t.plan;
+  // spec_mode 1: planning ahead (side stream, concurrently with the frame chain) for an assumed length;
+  // spec_mode 2: the real length is known: if it equals the assumed one the tables stand, otherwise plan again
+  if (threadIdx.x == 0) {
+    int hit = 0;
+    if (spec_mode == 2 && d_ndet && P->spec_state == 1 && P->valid > 0 && P->L_total == *d_ndet * PN) hit = 1;
+    s_hit = hit;
+    if (hit) P->spec_state = 2;
+  }
+  __syncthreads();
+  if (s_hit) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nq = (int)g.nq;
   const int win = (int)g.win, hop = (int)g.hop, nov = win - hop;
@@ -54,9 +65,10 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
         got += take;
       }
       L = total; Lloc = mine; Lav = mine + got; sample_offset = soff;
-    } else if (d_ndet) { L = *d_ndet * PN; Lloc = L; Lav = L; }
+    } else if (d_ndet && spec_mode != 1) { L = *d_ndet * PN; Lloc = L; Lav = L; }
     P->L_total = L; P->sample_offset = sample_offset; P->L_avail = Lav;
     P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0; P->task_counter = 0; P->ticket_r = 0; P->ticket_h = 0;
+    P->spec_state = (spec_mode == 1) ? 1 : 0;
     int ok = (L >= (unsigned long long)win) ? 1 : 0;
     int lg = (L <= 1) ? 0 : 64 - __clzll((long long)(L - 1));
     unsigned long long nfft = 1ull << lg;
@@ -189,9 +201,9 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
 }
 
 // full coefficient table [nb][2*half] and the window DC response per bin for the CUDA-core kernels
-__global__ void __launch_bounds__(256) stft_coef_kernel(StftTables t, StftGeom g) {
+__global__ void __launch_bounds__(256) stft_coef_kernel(StftTables t, StftGeom g, int spec_mode) {
   const StftPlan* P = t.plan;
-  if (P->valid <= 0) return;
+  if (P->valid <= 0 || (spec_mode == 2 && P->spec_state == 2)) return;
   const int nb = P->nb, win = (int)g.win, half = win / 2, odd = win & 1;
   const unsigned long long nfft = P->nfft;
   const long long mod = (long long)(2 * nfft);
@@ -745,12 +757,12 @@ int stft_variant() {
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st, const double* gathered, uint32_t world, uint32_t rank, sig_t* xc) {
+                             cudaStream_t st, const double* gathered, uint32_t world, uint32_t rank, sig_t* xc, int spec_mode) {
   const bool tc = (g.win == 20 && stft_variant() < 0);
   stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks,
-                                       tc ? 2 : 0, gathered, world, rank, xc);
-  if (!tc) { stft_coef_kernel<<<128, 256, 0, st>>>(t, g); return cudaGetLastError(); }
-  return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st);
+                                       tc ? 2 : 0, gathered, world, rank, xc, spec_mode);
+  if (!tc) { stft_coef_kernel<<<128, 256, 0, st>>>(t, g, spec_mode); return cudaGetLastError(); }
+  return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st, spec_mode);
   return cudaGetLastError();
 }
 

@@ -166,9 +166,9 @@ __device__ __forceinline__ void flush_rows(uint32_t a_stage, int ncols_valid, fl
 // the matrices Chi | Clo | Shi | Slo in the UMMA layout
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, StftGeom g, float* __restrict__ tcB, int BN,
-                                                              int n_chunk_cap) {
+                                                              int n_chunk_cap, int spec_mode) {
   const StftPlan* P = t.plan;
-  if (P->valid <= 0) return;
+  if (P->valid <= 0 || (spec_mode == 2 && P->spec_state == 2)) return;   // tables of the look-ahead plan stand
   const int nb = P->nb;
   const int step = BN - 1;
   const int n_chunks = (nb - 1 + step - 1) / step;
@@ -513,10 +513,10 @@ size_t stft_tc_table_bytes(int nb_max) {
 size_t stft_tc_meta_bytes(int) { return 16; }
 
 cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t*, int nb_max,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, int spec_mode) {
   const int bn = tc_shape_bn();
   const int n_chunk_cap = (nb_max - 1 + bn - 2) / (bn - 1) + 1;
-  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, bn, n_chunk_cap);
+  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, bn, n_chunk_cap, spec_mode);
   return cudaGetLastError();
 }
 
