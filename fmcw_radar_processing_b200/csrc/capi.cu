@@ -138,7 +138,7 @@ struct fmcw_handle {
   StftGeom geom{};
   DevBuf plan, bins, kcb, wdc, qpos, aq, qend, coef, swin, hard, derr;
   // scratch
-  DevBuf shard_geom, tcb, tcmeta, colub;
+  DevBuf tcb, colub;
   DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, o_slow64, f32_stage, xc, det_list, ndet, inten, synth_tab;
   // state
   uint64_t n_frames = 0;
@@ -213,7 +213,6 @@ void fill_tables(fmcw_handle* h) {
   h->st.win = h->swin.as<float>();
   h->st.hard_list = h->hard.as<unsigned int>();
   h->st.tcB = h->tcb.as<float>();
-  h->st.tc_meta = h->tcmeta.as<uint32_t>();
 }
 
 fmcw_status read_info(fmcw_handle* h) {
@@ -535,8 +534,8 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   ok(h->coef.ensure((size_t)nb_max * 2 * half * 4 + 64));
   h->st.hard_cap = 1u << 20;
   ok(h->hard.ensure((size_t)h->st.hard_cap * 4));
-  ok(h->tcb.ensure(stft_tc_table_bytes(nb_max) + 256)); ok(h->tcmeta.ensure(stft_tc_meta_bytes(nb_max) + 256));
-  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16)); ok(h->shard_geom.ensure(sizeof(ShardGeom)));
+  ok(h->tcb.ensure(stft_tc_table_bytes(nb_max) + 256));
+  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16));
   if (e == cudaSuccess) {
     ok(cudaMemsetAsync(h->plan.p, 0, sizeof(StftPlan), h->stream));
     ok(cudaMemsetAsync(h->derr.p, 0, 16, h->stream));
@@ -557,7 +556,7 @@ void fmcw_destroy(fmcw_handle* h) {
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
-                   &h->synth_tab, &h->shard_geom, &h->tcb, &h->tcmeta, &h->colub};
+                   &h->synth_tab, &h->tcb, &h->colub};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
   if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }

@@ -80,7 +80,6 @@ struct StftTables {             // device arrays owned by the handle
   unsigned int hard_cap;
   float* col_ub;                // [local columns] trivial upper bound 2*(sum|y|)^2 of each column's maximum
   float* tcB;                   // tensor-core path: per 128-bin chunk Chi|Clo|Shi|Slo in the UMMA smem layout
-  uint32_t* tc_meta;            // tensor-core path: per chunk column {doubling flag, first query, #queries}
   int nb_max;
 };
 
@@ -90,8 +89,6 @@ struct StftGeom {
   float rho;   // rigorous bound of max_{w >= pi/(win-1)} |W(w)| / W(0) of the STFT window (host, float64)
 };
 
-// sizes of a sharded run, resolved on the device from the all-gathered shard headers
-struct ShardGeom { unsigned long long L_total, sample_offset, L_local, L_avail; };
 
 
 cudaError_t launch_shard_pack(const sig_t* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win, double* msg,
@@ -111,11 +108,10 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t
 
 // tensor-core (tcgen05) STFT main kernel, window_length = 20 (stft_tc.cu)
 size_t stft_tc_table_bytes(int nb_max);
-size_t stft_tc_meta_bytes(int nb_max);
-cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t* tc_meta, int nb_max,
-                                   cudaStream_t st, int spec_mode = 0);
+cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, int nb_max, cudaStream_t st,
+                                   int spec_mode = 0);
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
-                                const uint32_t* tc_meta, unsigned long long capacity_cols, unsigned long long ld_cols,
+                                unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev = nullptr);
 int stft_variant();            // FMCW_STFT_VARIANT: -1 (default) tensor cores, 0..4 CUDA-core variants
 

@@ -762,7 +762,7 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
   stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks,
                                        tc ? 2 : 0, gathered, world, rank, xc, spec_mode);
   if (!tc) { stft_coef_kernel<<<128, 256, 0, st>>>(t, g, spec_mode); return cudaGetLastError(); }
-  return launch_stft_tc_prepare(t, g, t.tcB, t.tc_meta, t.nb_max, st, spec_mode);
+  return launch_stft_tc_prepare(t, g, t.tcB, t.nb_max, st, spec_mode);
   return cudaGetLastError();
 }
 
@@ -803,7 +803,7 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t
                              cudaStream_t st, const double* gmax_dev) {
   const int sms = sm_count();
   if (g.win == 20 && stft_variant() < 0)
-    return launch_stft_tc_main(t, g, x, out, t.tcB, t.tc_meta, capacity_cols, ld_cols, layout, d_err, st, gmax_dev);
+    return launch_stft_tc_main(t, g, x, out, t.tcB, capacity_cols, ld_cols, layout, d_err, st, gmax_dev);
   if (gmax_dev) {
     cudaError_t e0 = launch_stft_set_max_dev(t, gmax_dev, st);
     if (e0 != cudaSuccess) return e0;

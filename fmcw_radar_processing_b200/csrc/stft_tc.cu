@@ -32,7 +32,6 @@ constexpr float K_DB = 6.020599913279624f;
 constexpr int TC_HALF = 10, TC_KP = 16;
 constexpr int TC_M = 128;
 constexpr int TC_A_MAT_BYTES = TC_M * TC_KP * 4;     // 8 KB per A operand matrix
-constexpr int TC_QF = 16;
 
 // Kernel shape: BN bins per chunk (the N of the UMMA tile), EW epilogue warps, CTAS resident CTAs per SM.
 //   <128, 16, 1>: one CTA per SM, everything double buffered;
@@ -138,25 +137,6 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   return r;
 }
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-
-// staged [32 columns][16 queries] tile of one warp -> (up to) 64-byte rows of the time-major spectrogram;
-// slots [first, nvalid) of the row are valid
-__device__ __forceinline__ void flush_rows(uint32_t a_stage, int ncols_valid, float* __restrict__ out_warp,
-                                           unsigned long long row_stride, int qbase, int first, int nvalid, int lane) {
-  __syncwarp();
-  const int sub = lane >> 4, ql = lane & 15;
-  float* ptr = out_warp + (unsigned long long)sub * row_stride + qbase + ql;
-  uint32_t a = a_stage + (uint32_t)((sub * (TC_QF + 1) + ql) * 4);
-  if (ql >= first && ql < nvalid) {
-#pragma unroll 4
-    for (int c = sub; c < ncols_valid; c += 2) {
-      *ptr = lds32(a);
-      ptr += 2 * row_stride;
-      a += 2 * (TC_QF + 1) * 4;
-    }
-  }
-  __syncwarp();
-}
 
 }  // namespace
 
@@ -510,10 +490,9 @@ size_t stft_tc_table_bytes(int nb_max) {
   const size_t c64 = (size_t)((nb_max - 1 + 62) / 63 + 1) * 64, c128 = (size_t)((nb_max - 1 + 126) / 127 + 1) * 128;
   return (c64 > c128 ? c64 : c128) * TC_KP * 4 * 4;
 }
-size_t stft_tc_meta_bytes(int) { return 16; }
 
-cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, uint32_t*, int nb_max,
-                                   cudaStream_t st, int spec_mode) {
+cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, int nb_max, cudaStream_t st,
+                                   int spec_mode) {
   const int bn = tc_shape_bn();
   const int n_chunk_cap = (nb_max - 1 + bn - 2) / (bn - 1) + 1;
   stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, bn, n_chunk_cap, spec_mode);
@@ -531,7 +510,7 @@ static cudaError_t launch_tc_shape(const StftTables& t, const StftGeom& g, const
 }
 
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
-                                const uint32_t*, unsigned long long capacity_cols, unsigned long long ld_cols,
+                                unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
