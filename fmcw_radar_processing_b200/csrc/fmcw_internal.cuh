@@ -64,6 +64,9 @@ struct StftPlan {
   double pmax_raw;              // final global max of c_j |S|^2
   int chunk_q0[MAX_CHUNKS + 1]; // query range of each chunk (multiples of 32 except the last end)
   int chunk_p0[MAX_CHUNKS + 1]; // first bin position each chunk needs
+  int tc_nch;                   // tensor-core path: chunks of whole 32-query blocks (stft_tc_prepare_kernel)
+  int tc_q0[MAX_CHUNKS + 1];    // first query of each chunk (multiples of 32; [tc_nch] = nq)
+  int tc_p0[MAX_CHUNKS + 1];    // bin position of each chunk's column 0
 };
 
 struct StftTables {             // device arrays owned by the handle

@@ -5,7 +5,8 @@
 // with E/O the even/odd folded, windowed taps of a spectrogram column.  On the fp32 pipe this costs 20 FMAs
 // per 4-byte output and bounds the kernel at ~50 % FMA-pipe utilisation (profiles/ncu_full_r1b.txt).  Here:
 //   * one CTA tile = 128 spectrogram columns (the M = 128 rows of the UMMA tile, one TMEM lane each);
-//   * bins are walked in chunks of 128 (N = 128, one bin of overlap): Re and Im accumulators = 256 TMEM columns;
+//   * bins are walked in chunks of up to 128 (N = 128): Re and Im accumulators = 256 TMEM columns; a chunk covers
+//     whole blocks of 32 log-frequency queries (both brackets of each), so the interp1 phase never splits a block;
 //   * operands are split hi + lo in TF32 (cvt.rna) and three products hi*hi + hi*lo + lo*hi are accumulated
 //     in fp32 -- ~2^-22 relative, the float32 class of the CUDA-core kernel (single-pass TF32/BF16 would not
 //     meet the 1e-3 dB tolerance);
@@ -43,15 +44,19 @@ struct TcShape {
   static constexpr int SW = EW / 4;                    // warps per TMEM lane quarter
   static constexpr int CW = 32 / SW;                   // spectrogram columns per warp in the interp1 phase
   static constexpr int THREADS = (EW + 2) * 32;
-  static constexpr int STEP = BN - 1;                  // new bin positions per chunk (one position of overlap)
   static constexpr int B_MAT_BYTES = BN * TC_KP * 4;
   static constexpr int B_BYTES = 4 * B_MAT_BYTES;      // Chi | Clo | Shi | Slo
   static constexpr int ABUF = (CTAS == 1) ? 2 : 1;     // A tile buffers
-  static constexpr int DBS = BN + 2;                   // dB row stride: 8-byte aligned, conflict-free both ways
+  // dB rows keep even and odd bin positions in two planes (odd plane at DB_OFF words): where every query has
+  // its own bracket pair (positions step by 2, most of the axis) 32 consecutive queries read 32 consecutive
+  // words of each plane.  DB_OFF = 16 (mod 32) keeps the planes apart where positions step by 0/1; the row
+  // stride = 2 (mod 32) makes the 64-bit stores of the dB phase (lanes = columns) conflict free.
+  static constexpr int DB_OFF = BN / 2 + 16;
+  static constexpr int DBS = ((BN + 16 - 2 + 31) / 32) * 32 + 2;
   static constexpr int TMEM_COLS = 4 * BN;             // two stages of (Re | Im)
   static constexpr int OFF_B = ABUF * 4 * TC_A_MAT_BYTES;
   static constexpr int OFF_AQ = OFF_B + 2 * B_BYTES;
-  static constexpr int N_F32 = MAX_NQ + 32 + MAX_NQ + 64 + 4 * 32 * DBS;
+  static constexpr int N_F32 = MAX_NQ + 32 + MAX_NQ + 128 + 4 * 32 * DBS;
   static constexpr int OFF_BAR = OFF_AQ + ((N_F32 + 3) / 4) * 16;
   static constexpr int SMEM = OFF_BAR + 16 * 8 + 16;
 };
@@ -141,18 +146,41 @@ __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.sh
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// B operands: chunk c covers bin positions [c*(BN-1), c*(BN-1)+BN) (one position of overlap, so that every
-// chunk carries the bin preceding its first new bin: the lower bracket of the first interp1 interval); per chunk
-// the matrices Chi | Clo | Shi | Slo in the UMMA layout
+// Chunk table + B operands.  A chunk = up to BN consecutive bin positions that hold both brackets of a whole number
+// of 32-query blocks (greedy; a block needs at most 64 positions, so it always fits); per chunk the matrices
+// Chi | Clo | Shi | Slo in the UMMA layout.  Every CTA derives the (tiny) table itself; CTA 0 publishes it.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, StftGeom g, float* __restrict__ tcB, int BN,
-                                                              int n_chunk_cap, int spec_mode) {
-  const StftPlan* P = t.plan;
+                                                              int spec_mode) {
+  StftPlan* P = t.plan;
   if (P->valid <= 0 || (spec_mode == 2 && P->spec_state == 2)) return;   // tables of the look-ahead plan stand
-  const int nb = P->nb;
-  const int step = BN - 1;
-  const int n_chunks = (nb - 1 + step - 1) / step;
-  if (n_chunks > n_chunk_cap) return;
+  __shared__ int s_s[MAX_CHUNKS], s_e[MAX_CHUNKS], s_p0[MAX_CHUNKS + 1], s_q0[MAX_CHUNKS + 1], s_n;
+  const int nb = P->nb, nq = P->nq;
+  const int nblk = (nq + 31) >> 5;
+  if ((int)threadIdx.x < nblk) {
+    const int qa = 32 * threadIdx.x, qb = min(qa + 32, nq);
+    s_s[threadIdx.x] = t.qpos[qa];
+    s_e[threadIdx.x] = t.qpos[qb - 1] + 2;            // positions [s, e): lower bracket of qa .. upper bracket of qb-1
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0, b = 0;
+    while (b < nblk) {
+      const int p0 = s_s[b];
+      int e = b + 1;
+      while (e < nblk && s_e[e] - p0 <= BN) ++e;
+      s_p0[n] = p0; s_q0[n] = 32 * b;
+      ++n; b = e;
+    }
+    s_p0[n] = nb; s_q0[n] = nq;
+    s_n = n;
+    if (blockIdx.x == 0) {
+      P->tc_nch = n;
+      for (int i = 0; i <= n; ++i) { P->tc_p0[i] = s_p0[i]; P->tc_q0[i] = s_q0[i]; }
+    }
+  }
+  __syncthreads();
+  const int n_chunks = s_n;
   const unsigned long long nfft = P->nfft;
   const long long mod = (long long)(2 * nfft);
   const int total = n_chunks * BN * TC_KP;
@@ -160,7 +188,7 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % TC_KP, idx = i / TC_KP;
     const int ch = idx / BN, n = idx % BN;
-    const int pos = ch * step + n;
+    const int pos = s_p0[ch] + n;
     double cv = 0.0, sv = 0.0;
     if (pos < nb) {
       const long long bin = t.bins[pos];
@@ -194,7 +222,7 @@ __global__ void __launch_bounds__(S::THREADS, S::CTAS)
 stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
                unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, int dbg_mode,
                const double* __restrict__ gmax_dev) {
-  constexpr int BN = S::BN, EW = S::EW, SW = S::SW, CW = S::CW, STEP = S::STEP, DBS = S::DBS, ABUF = S::ABUF;
+  constexpr int BN = S::BN, EW = S::EW, SW = S::SW, CW = S::CW, DBS = S::DBS, DB_OFF = S::DB_OFF, ABUF = S::ABUF;
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
   extern __shared__ __align__(128) unsigned char smem[];
@@ -204,7 +232,8 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   float* s_ws = s_aq + MAX_NQ;                                         // [32] normalised window
   int* s_qpos = reinterpret_cast<int*>(s_ws + 32);                     // [MAX_NQ] position of each query's lower bracket
   int* s_qrng = s_qpos + MAX_NQ;                                       // [64] first query of every chunk
-  float* s_db = reinterpret_cast<float*>(s_qrng + 64);                 // [4 quarters][32 columns][DBS] dB of a chunk
+  int* s_cp0 = s_qrng + 64;                                            // [64] bin position of column 0 of every chunk
+  float* s_db = reinterpret_cast<float*>(s_cp0 + 64);                 // [4 quarters][32 columns][DBS] dB of a chunk
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
 
@@ -213,7 +242,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   const unsigned long long ncl = ce - cb;
   if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
   const int nq = P->nq, nb = P->nb;
-  const int n_chunks = (nb - 1 + STEP - 1) / STEP;
+  const int n_chunks = P->tc_nch;
   const unsigned long long n_tiles = (ncl + TC_M - 1) / TC_M;
   // normalisation max(P): the plan's own search, or the all-reduced value of a sharded run
   const double pmax = gmax_dev ? *gmax_dev : P->pmax_raw;
@@ -235,9 +264,9 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < nq; i += S::THREADS) { s_aq[i] = t.aq[i]; s_qpos[i] = t.qpos[i]; }
-  if (tid <= n_chunks && tid < 64) {   // queries [s_qrng[ch], s_qrng[ch+1]) have their bracket inside chunk ch
-    const int p = tid * STEP;
-    s_qrng[tid] = t.qend[p < nb ? p : nb];
+  if (tid <= n_chunks && tid < 64) {   // queries [s_qrng[ch], s_qrng[ch+1]) have both brackets inside chunk ch
+    s_qrng[tid] = P->tc_q0[tid];
+    s_cp0[tid] = P->tc_p0[tid];
   }
   if (tid < 2 * TC_HALF) s_ws[tid] = (float)((double)t.win[tid] / sqrt(pmax));
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -318,7 +347,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
         const int ts = (int)(cseq & 1);
         const int gi = (sw + ch) % SW;                      // 32-bin group of this chunk converted to dB by this warp
-        const int pos_c0 = ch * STEP;                       // bin position of chunk column 0
+        const int pos_c0 = s_cp0[ch];                       // bin position of chunk column 0
         mbar_wait(BAR(8 + ts), (uint32_t)((cseq >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
@@ -343,20 +372,25 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           if (dbg_mode == 1) { if (re[0] + im[31] == 123.456f) out[0] = 1.f; continue; }
           // |S|^2 -> dB of 32 bins (independent chains, two bins per packed FMUL2 / FFMA2), one-sided doubling for
           // all bins; the (at most two) un-doubled positions are corrected below
-          const uint32_t a_row = a_db + (uint32_t)((lane * DBS + gi * 32) * 4);
+          // even positions of the chunk go to the first plane of the row, odd ones to the plane at DB_OFF
+          const uint32_t a_row = a_db + (uint32_t)((lane * DBS + gi * 16) * 4);
           const float2 kk = make_float2(K_DB, K_DB);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 r2 = make_float2(re[j], re[j + 1]), i2 = make_float2(im[j], im[j + 1]);
-            const float2 p2 = fma2(r2, r2, mul2(i2, i2));
-            const float2 l2 = make_float2(lg2_approx(p2.x), lg2_approx(p2.y));
-            sts64(a_row + (uint32_t)(j * 4), fma2(kk, l2, kk));
+          for (int j = 0; j < 32; j += 4) {
+            const float2 ra = make_float2(re[j], re[j + 1]), ia = make_float2(im[j], im[j + 1]);
+            const float2 rb = make_float2(re[j + 2], re[j + 3]), ib = make_float2(im[j + 2], im[j + 3]);
+            const float2 pa = fma2(ra, ra, mul2(ia, ia)), pb = fma2(rb, rb, mul2(ib, ib));
+            const float2 le = make_float2(lg2_approx(pa.x), lg2_approx(pb.x));   // positions j, j+2
+            const float2 lo = make_float2(lg2_approx(pa.y), lg2_approx(pb.y));   // positions j+1, j+3
+            sts64(a_row + (uint32_t)(j * 2), fma2(kk, le, kk));
+            sts64(a_row + (uint32_t)(DB_OFF * 4 + j * 2), fma2(kk, lo, kk));
           }
           const int p_lo = pos_c0 + gi * 32;
           if ((sp0 >= p_lo && sp0 < p_lo + 32) || (sp1 >= p_lo && sp1 < p_lo + 32)) {
             __syncwarp();
             const int sp = (sp0 >= p_lo && sp0 < p_lo + 32) ? sp0 : sp1;
-            const uint32_t aa = a_db + (uint32_t)((lane * DBS + (sp - pos_c0)) * 4);
+            const int rp = sp - pos_c0;
+            const uint32_t aa = a_db + (uint32_t)((lane * DBS + (rp >> 1) + (rp & 1) * DB_OFF) * 4);
             sts32(aa, lds32(aa) - K_DB);
           }
         }
@@ -372,7 +406,8 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
             const bool ok = q >= Qa && q < Qb;
             const int jl = ok ? __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0 : 0;
             const float a = lds32(a_aq + 4 * q);
-            const uint32_t ad = a_db + (uint32_t)((c_lo * DBS + jl) * 4);
+            const uint32_t ad = a_db + (uint32_t)((c_lo * DBS + (jl >> 1) + (jl & 1) * DB_OFF) * 4);           // lower bracket
+            const uint32_t au = a_db + (uint32_t)((c_lo * DBS + ((jl + 1) >> 1) + ((jl + 1) & 1) * DB_OFF) * 4);  // upper bracket
             if (NQC > 0 && ncols_valid == 32) {
               float* ptr = out_warp + (unsigned long long)c_lo * NQC + q;
 #pragma unroll
@@ -381,7 +416,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                   lo[c] = lds32(ad + (uint32_t)((c8 + c) * DBS * 4));
-                  hi[c] = lds32(ad + (uint32_t)((c8 + c) * DBS * 4 + 4));
+                  hi[c] = lds32(au + (uint32_t)((c8 + c) * DBS * 4));
                 }
                 if (ok && dbg_mode != 3) {
 #pragma unroll
@@ -396,7 +431,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
             } else if (ok) {
               float* ptr = out_warp + (unsigned long long)c_lo * nq + q;
               for (int c = 0; c < CW && c_lo + c < ncols_valid; ++c) {
-                const float lo = lds32(ad + (uint32_t)(c * DBS * 4)), hi = lds32(ad + (uint32_t)(c * DBS * 4 + 4));
+                const float lo = lds32(ad + (uint32_t)(c * DBS * 4)), hi = lds32(au + (uint32_t)(c * DBS * 4));
                 ptr[(unsigned long long)c * nq] = fmaf(a, hi - lo, lo);
               }
             }
@@ -409,7 +444,8 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
             for (int q = q0; q < q1; ++q) {
               const int jq = __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0;
               const float a = lds32(a_aq + 4 * q);
-              const float lo = lds32(ad + (uint32_t)(jq * 4)), hi = lds32(ad + (uint32_t)(jq * 4 + 4));
+              const float lo = lds32(ad + (uint32_t)(((jq >> 1) + (jq & 1) * DB_OFF) * 4));
+              const float hi = lds32(ad + (uint32_t)((((jq + 1) >> 1) + ((jq + 1) & 1) * DB_OFF) * 4));
               if (col_ok) out[(unsigned long long)q * ld_cols + (tile_col0 + m - cb)] = fmaf(a, hi - lo, lo);
             }
           }
@@ -486,16 +522,15 @@ static int tc_shape_bn() {
 }
 
 size_t stft_tc_table_bytes(int nb_max) {
-  // rows = chunks * BN; the BN = 64 shape has the most chunks
-  const size_t c64 = (size_t)((nb_max - 1 + 62) / 63 + 1) * 64, c128 = (size_t)((nb_max - 1 + 126) / 127 + 1) * 128;
-  return (c64 > c128 ? c64 : c128) * TC_KP * 4 * 4;
+  // at most one chunk per block of 32 queries, BN <= 128 rows each, four matrices of TC_KP floats per row
+  (void)nb_max;
+  return (size_t)MAX_CHUNKS * 128 * TC_KP * 4 * 4;
 }
 
 cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, int nb_max, cudaStream_t st,
                                    int spec_mode) {
-  const int bn = tc_shape_bn();
-  const int n_chunk_cap = (nb_max - 1 + bn - 2) / (bn - 1) + 1;
-  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, bn, n_chunk_cap, spec_mode);
+  (void)nb_max;
+  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, tc_shape_bn(), spec_mode);
   return cudaGetLastError();
 }
 
