@@ -64,9 +64,6 @@ struct StftPlan {
   double pmax_raw;              // final global max of c_j |S|^2
   int chunk_q0[MAX_CHUNKS + 1]; // query range of each chunk (multiples of 32 except the last end)
   int chunk_p0[MAX_CHUNKS + 1]; // first bin position each chunk needs
-  int tc_nch;                   // tensor-core path: chunks of whole 32-query blocks (stft_tc_prepare_kernel)
-  int tc_q0[MAX_CHUNKS + 1];    // first query of each chunk (multiples of 32; [tc_nch] = nq)
-  int tc_p0[MAX_CHUNKS + 1];    // bin position of each chunk's column 0
 };
 
 struct StftTables {             // device arrays owned by the handle
@@ -82,7 +79,7 @@ struct StftTables {             // device arrays owned by the handle
   unsigned int* hard_list;      // columns whose max needs the exhaustive search
   unsigned int hard_cap;
   float* col_ub;                // [local columns] trivial upper bound 2*(sum|y|)^2 of each column's maximum
-  float* tcB;                   // tensor-core path: per 128-bin chunk Chi|Clo|Shi|Slo in the UMMA smem layout
+  float* tcB;                   // tensor-core path: per chunk of 64 queries the B operands C|S in the UMMA smem layout
   int nb_max;
 };
 

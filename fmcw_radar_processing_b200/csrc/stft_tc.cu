@@ -1,26 +1,30 @@
 // STFT main kernel on the 5th-generation tensor cores (tcgen05 + TMEM), window_length = 20.
 //
-// The 20-tap windowed DTFT at the ~1.1k-1.7k planned bins (see stft.cu) is the contraction
+// The 20-tap windowed DTFT at the two fine-grid bins bracketing every log-frequency query (see stft.cu) is the
+// contraction
 //     Re[col][bin] = sum_k E[col][k] * C[bin][k],   Im[col][bin] = sum_k O[col][k] * S[bin][k]
 // with E/O the even/odd folded, windowed taps of a spectrogram column.  On the fp32 pipe this costs 20 FMAs
 // per 4-byte output and bounds the kernel at ~50 % FMA-pipe utilisation (profiles/ncu_full_r1b.txt).  Here:
 //   * one CTA tile = 128 spectrogram columns (the M = 128 rows of the UMMA tile, one TMEM lane each);
-//   * bins are walked in chunks of up to 128 (N = 128): Re and Im accumulators = 256 TMEM columns; a chunk covers
-//     whole blocks of 32 log-frequency queries (both brackets of each), so the interp1 phase never splits a block;
-//   * operands are split hi + lo in TF32 (cvt.rna) and three products hi*hi + hi*lo + lo*hi are accumulated
-//     in fp32 -- ~2^-22 relative, the float32 class of the CUDA-core kernel (single-pass TF32/BF16 would not
-//     meet the 1e-3 dB tolerance);
-//   * the column mean is removed before the split and returns as an extra tap (k = 10: mean * window DC
-//     response W(w_bin), tabulated in float64), so the large DC term is never rounded together with the
-//     small residual;
-//   * K = 10 (+1) taps are padded to 16 = two K = 8 TF32 instructions; 12 tcgen05.mma per chunk;
+//   * a chunk = 64 consecutive queries = 128 bins laid out as (lower, upper) bracket pairs (N = 128); Re and Im
+//     accumulators = 256 TMEM columns.  The layout is static, so the epilogue needs no index tables: a thread
+//     reads 32 accumulator columns = 16 queries, and the interp1 is register arithmetic;
+//   * operands are split hi + lo in TF32 (cvt.rna) and the three products hi*hi + hi*lo + lo*hi are laid side
+//     by side along K (10 taps x 3 + 2 DC slots = 32 = four K = 8 instructions per part, 8 tcgen05.mma per
+//     chunk), accumulated in fp32 -- ~2^-22 relative, the float32 class (single-pass TF32/BF16 would not meet
+//     the 1e-3 dB tolerance);
+//   * a TF32-exact estimate of the column mean is removed before the split and returns as the DC slots
+//     (mean * window DC response W(w_bin), tabulated in float64 and split hi + lo), so the large DC term is
+//     never rounded together with the small residual;
+//   * the one-sided doubling (RP:276) is folded into the B operands (sqrt(2) on every bin but DC and Nyquist);
 //   * A tiles are written to shared memory by the epilogue threads (K-major, no swizzle, core matrices of
 //     8 rows x 16 bytes); B tiles (planned once on the device) arrive by 1-D bulk copy (cp.async.bulk) on an
 //     mbarrier; tcgen05.commit signals the epilogue, which reads the accumulators with tcgen05.ld, takes
-//     |S|^2 -> lg2 -> dB, runs the interp1 onto the log-frequency axis and writes the spectrogram.
+//     |S|^2 -> lg2, interpolates, scales to dB and writes the spectrogram.
 // One CTA per SM (576 threads): warps 0-15 epilogue (lane quarter = warp & 3; the four warps of a quarter each
-// take one 32-bin group of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer.  TMEM (512 columns),
-// the A tiles and the B tiles are double buffered, so the MMAs of chunk c+1 overlap the epilogue of chunk c.
+// take 16 queries of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer.  TMEM (512 columns), the A
+// tiles, the B tiles and the output staging rows are double buffered: the MMAs of chunk c+1 and the stores of
+// chunk c-1 overlap the lg2 phase of chunk c.
 #include <cstdlib>
 
 #include "fmcw_internal.cuh"
@@ -29,39 +33,28 @@ namespace fmcw {
 
 namespace {
 
-constexpr float K_DB = 6.020599913279624f;
-constexpr int TC_HALF = 10, TC_KP = 16;
-constexpr int TC_M = 128;
-constexpr int TC_A_MAT_BYTES = TC_M * TC_KP * 4;     // 8 KB per A operand matrix
-
-// Kernel shape: BN bins per chunk (the N of the UMMA tile), EW epilogue warps, CTAS resident CTAs per SM.
-//   <128, 16, 1>: one CTA per SM, everything double buffered;
-//   < 64,  8, 2>: two independent CTAs per SM, so that one CTA's dB phase (XU bound) overlaps the other's
-//                 interp1 / store phase (LSU bound) -- the default.
-template <int BN_, int EW_, int CTAS_>
-struct TcShape {
-  static constexpr int BN = BN_, EW = EW_, CTAS = CTAS_;
-  static constexpr int SW = EW / 4;                    // warps per TMEM lane quarter
-  static constexpr int CW = 32 / SW;                   // spectrogram columns per warp in the interp1 phase
-  static constexpr int THREADS = (EW + 2) * 32;
-  static constexpr int B_MAT_BYTES = BN * TC_KP * 4;
-  static constexpr int B_BYTES = 4 * B_MAT_BYTES;      // Chi | Clo | Shi | Slo
-  static constexpr int ABUF = (CTAS == 1) ? 2 : 1;     // A tile buffers
-  // dB rows keep even and odd bin positions in two planes (odd plane at DB_OFF words): where every query has
-  // its own bracket pair (positions step by 2, most of the axis) 32 consecutive queries read 32 consecutive
-  // words of each plane.  DB_OFF = 16 (mod 32) keeps the planes apart where positions step by 0/1; the row
-  // stride = 2 (mod 32) makes the 64-bit stores of the dB phase (lanes = columns) conflict free.
-  static constexpr int DB_OFF = BN / 2 + 16;
-  static constexpr int DBS = ((BN + 16 - 2 + 31) / 32) * 32 + 2;
-  static constexpr int TMEM_COLS = 4 * BN;             // two stages of (Re | Im)
-  static constexpr int OFF_B = ABUF * 4 * TC_A_MAT_BYTES;
-  static constexpr int OFF_AQ = OFF_B + 2 * B_BYTES;
-  static constexpr int N_F32 = MAX_NQ + 32 + MAX_NQ + 128 + 4 * 32 * DBS;
-  static constexpr int OFF_BAR = OFF_AQ + ((N_F32 + 3) / 4) * 16;
-  static constexpr int SMEM = OFF_BAR + 16 * 8 + 16;
-};
-static_assert(TcShape<128, 16, 1>::BN / TcShape<128, 16, 1>::SW == 32 && TcShape<64, 8, 2>::BN / TcShape<64, 8, 2>::SW == 32,
-              "every epilogue warp converts 32 bins of a chunk");
+constexpr float K_DB = 6.020599913279624f;            // 20 log10(2): dB per octave of the (power) ratio, RP:283
+constexpr int TC_HALF = 10;                            // folded taps
+constexpr int TC_M = 128, TC_N = 128, TC_K = 32;       // UMMA tile; K = 3 x 10 taps + 2 DC slots
+constexpr int TC_QC = TC_N / 2;                        // queries per chunk
+constexpr int TC_EW = 16;                              // epilogue warps
+constexpr int TC_THREADS = (TC_EW + 2) * 32;
+constexpr int TC_A_MAT_BYTES = TC_M * TC_K * 4;        // 16 KB per A operand matrix (E or O)
+constexpr int TC_A_BYTES = 2 * TC_A_MAT_BYTES;
+constexpr int TC_B_MAT_BYTES = TC_N * TC_K * 4;        // 16 KB per B operand matrix (C or S)
+constexpr int TC_B_BYTES = 2 * TC_B_MAT_BYTES;
+constexpr int TC_TMEM_COLS = 4 * TC_N;                 // two stages of (Re | Im)
+// output staging: [buffer][quarter][column][64 queries], row stride = 4 (mod 32) words: conflict-free 128-bit
+// stores by column and conflict-free 64-bit loads by query
+constexpr int TC_SROW = TC_QC + 4;
+constexpr int TC_SQ = 32 * TC_SROW;                    // floats per quarter
+constexpr int TC_SBUF = 4 * TC_SQ;                     // floats per buffer
+constexpr int TC_OFF_B = 2 * TC_A_BYTES;
+constexpr int TC_OFF_STG = TC_OFF_B + 2 * TC_B_BYTES;
+constexpr int TC_OFF_AQ = TC_OFF_STG + 2 * TC_SBUF * 4;
+constexpr int TC_OFF_BAR = TC_OFF_AQ + (MAX_NQ + 32) * 4;
+constexpr int TC_SMEM = TC_OFF_BAR + 16 * 8 + 16;
+static_assert(MAX_NQ % TC_QC == 0, "query table is padded to whole chunks");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -76,13 +69,13 @@ __device__ __forceinline__ float lg2_approx(float x) {
 }
 // canonical K-major, non-swizzled operand layout: (row/8)*SBO + (k/4)*128 + (row%8)*16 + (k%4)*4 bytes
 __host__ __device__ __forceinline__ int tc_off_floats(int row, int k) {
-  return (row >> 3) * (TC_KP * 8) + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
+  return (row >> 3) * (TC_K * 8) + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)(128u >> 4) << 16;                 // leading byte offset: next 16-byte K chunk
-  d |= (uint64_t)((TC_KP * 32u) >> 4) << 32;        // stride byte offset: next group of 8 rows
+  d |= (uint64_t)((TC_K * 32u) >> 4) << 32;        // stride byte offset: next group of 8 rows
   d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell), no swizzle
   return d;
 }
@@ -114,13 +107,19 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+                 "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// wait for this thread's outstanding tcgen05.ld and tie the destination registers to the wait, so that no use of
+// them can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld(float (&a)[16], float (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  asm volatile("" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]),
+                    "+f"(a[8]), "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]));
+  asm volatile("" : "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]),
+                    "+f"(b[8]), "+f"(b[9]), "+f"(b[10]), "+f"(b[11]), "+f"(b[12]), "+f"(b[13]), "+f"(b[14]), "+f"(b[15]));
 }
 __device__ __forceinline__ float lds32(uint32_t a) {
   float v;
@@ -143,151 +142,144 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 }
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return r;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// Chunk table + B operands.  A chunk = up to BN consecutive bin positions that hold both brackets of a whole number
-// of 32-query blocks (greedy; a block needs at most 64 positions, so it always fits); per chunk the matrices
-// Chi | Clo | Shi | Slo in the UMMA layout.  Every CTA derives the (tiny) table itself; CTA 0 publishes it.
+// B operands.  Chunk c, row n: query 64c + n/2, lower (n even) or upper (n odd) bracket bin.  Along K:
+//   C: [Chi(10) | Clo(10) | Chi(10) | Whi | Wlo]     against A = [Ehi | Ehi | Elo | M | M]
+//   S: [Shi(10) | Slo(10) | Shi(10) |  0  |  0 ]     against A = [Ohi | Ohi | Olo | 0 | 0]
+// with cos/sin((k+1/2) w_bin) and the window DC response W(w_bin) in float64, times sqrt(2) for every bin that
+// the one-sided spectrum doubles.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, StftGeom g, float* __restrict__ tcB, int BN,
+__global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, StftGeom g, float* __restrict__ tcB,
                                                               int spec_mode) {
-  StftPlan* P = t.plan;
+  const StftPlan* P = t.plan;
   if (P->valid <= 0 || (spec_mode == 2 && P->spec_state == 2)) return;   // tables of the look-ahead plan stand
-  __shared__ int s_s[MAX_CHUNKS], s_e[MAX_CHUNKS], s_p0[MAX_CHUNKS + 1], s_q0[MAX_CHUNKS + 1], s_n;
-  const int nb = P->nb, nq = P->nq;
-  const int nblk = (nq + 31) >> 5;
-  if ((int)threadIdx.x < nblk) {
-    const int qa = 32 * threadIdx.x, qb = min(qa + 32, nq);
-    s_s[threadIdx.x] = t.qpos[qa];
-    s_e[threadIdx.x] = t.qpos[qb - 1] + 2;            // positions [s, e): lower bracket of qa .. upper bracket of qb-1
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int n = 0, b = 0;
-    while (b < nblk) {
-      const int p0 = s_s[b];
-      int e = b + 1;
-      while (e < nblk && s_e[e] - p0 <= BN) ++e;
-      s_p0[n] = p0; s_q0[n] = 32 * b;
-      ++n; b = e;
-    }
-    s_p0[n] = nb; s_q0[n] = nq;
-    s_n = n;
-    if (blockIdx.x == 0) {
-      P->tc_nch = n;
-      for (int i = 0; i <= n; ++i) { P->tc_p0[i] = s_p0[i]; P->tc_q0[i] = s_q0[i]; }
-    }
-  }
-  __syncthreads();
-  const int n_chunks = s_n;
+  const int nq = P->nq;
+  const int n_chunks = (nq + TC_QC - 1) / TC_QC;
   const unsigned long long nfft = P->nfft;
   const long long mod = (long long)(2 * nfft);
-  const int total = n_chunks * BN * TC_KP;
-  const int mat = BN * TC_KP;                    // floats per operand matrix
+  constexpr int NT = TC_HALF + 1;
+  constexpr int mat = TC_N * TC_K;               // floats per operand matrix
+  const int total = n_chunks * TC_N * NT;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int k = i % TC_KP, idx = i / TC_KP;
-    const int ch = idx / BN, n = idx % BN;
-    const int pos = s_p0[ch] + n;
+    const int k = i % NT, idx = i / NT;
+    const int ch = idx / TC_N, n = idx % TC_N;
+    const int q = ch * TC_QC + (n >> 1);
     double cv = 0.0, sv = 0.0;
-    if (pos < nb) {
-      const long long bin = t.bins[pos];
+    if (q < nq) {
+      const long long bin = (long long)t.bins[t.qpos[q]] + (n & 1);
+      const double sc = (bin == 0 || (unsigned long long)bin == nfft / 2) ? 1.0 : 1.4142135623730951;
       if (k < TC_HALF) {
         const long long r = ((long long)(2 * k + 1) * bin) % mod;
         sincospi((double)r / (double)nfft, &sv, &cv);
-      } else if (k == TC_HALF) {
+        sv *= sc;
+      } else {
         // window DC response at this bin: sum_m (w[9-m] + w[10+m]) cos((m+1/2) w)
         for (int m = 0; m < TC_HALF; ++m) {
           const long long r = ((long long)(2 * m + 1) * bin) % mod;
           cv += ((double)t.win[TC_HALF - 1 - m] + (double)t.win[TC_HALF + m]) * cospi((double)r / (double)nfft);
         }
       }
+      cv *= sc;
     }
     const float chi = tf32_rna((float)cv), shi = tf32_rna((float)sv);
     const float clo = tf32_rna((float)(cv - (double)chi)), slo = tf32_rna((float)(sv - (double)shi));
-    float* blk = tcB + (size_t)ch * (4 * mat);
-    const int off = tc_off_floats(n, k);
-    blk[off] = chi;
-    blk[mat + off] = clo;
-    blk[2 * mat + off] = shi;
-    blk[3 * mat + off] = slo;
+    float* C = tcB + (size_t)ch * (2 * mat);
+    float* S = C + mat;
+    if (k < TC_HALF) {
+      C[tc_off_floats(n, k)] = chi; C[tc_off_floats(n, TC_HALF + k)] = clo; C[tc_off_floats(n, 2 * TC_HALF + k)] = chi;
+      S[tc_off_floats(n, k)] = shi; S[tc_off_floats(n, TC_HALF + k)] = slo; S[tc_off_floats(n, 2 * TC_HALF + k)] = shi;
+    } else {
+      C[tc_off_floats(n, 3 * TC_HALF)] = chi; C[tc_off_floats(n, 3 * TC_HALF + 1)] = clo;
+      S[tc_off_floats(n, 3 * TC_HALF)] = 0.f; S[tc_off_floats(n, 3 * TC_HALF + 1)] = 0.f;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// main kernel: EW epilogue warps + MMA issuer + bulk-copy producer
+// main kernel: 16 epilogue warps + MMA issuer + bulk-copy producer
+//   LAYOUT 0: time-major out[col][query]; LAYOUT 1: frequency-major out[query][ld_cols].
+//   NQC: compile-time number of queries (1024) for the time-major fast path, 0 = run-time nq.
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT, int NQC, class S>
-__global__ void __launch_bounds__(S::THREADS, S::CTAS)
+template <int LAYOUT, int NQC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
                unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, int dbg_mode,
                const double* __restrict__ gmax_dev) {
-  constexpr int BN = S::BN, EW = S::EW, SW = S::SW, CW = S::CW, DBS = S::DBS, DB_OFF = S::DB_OFF, ABUF = S::ABUF;
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
   extern __shared__ __align__(128) unsigned char smem[];
-  float* sA = reinterpret_cast<float*>(smem);                          // ABUF x (Ehi | Elo | Ohi | Olo)
-  float* sB = reinterpret_cast<float*>(smem + S::OFF_B);               // 2 x (Chi | Clo | Shi | Slo)
-  float* s_aq = reinterpret_cast<float*>(smem + S::OFF_AQ);            // [MAX_NQ] interp1 weights
+  float* sA = reinterpret_cast<float*>(smem);                          // 2 x (E | O)
+  float* sB = reinterpret_cast<float*>(smem + TC_OFF_B);               // 2 x (C | S)
+  float* s_stg = reinterpret_cast<float*>(smem + TC_OFF_STG);          // 2 x [4 quarters][32 columns][TC_SROW]
+  float* s_aq = reinterpret_cast<float*>(smem + TC_OFF_AQ);            // [MAX_NQ] interp1 weights (zero padded)
   float* s_ws = s_aq + MAX_NQ;                                         // [32] normalised window
-  int* s_qpos = reinterpret_cast<int*>(s_ws + 32);                     // [MAX_NQ] position of each query's lower bracket
-  int* s_qrng = s_qpos + MAX_NQ;                                       // [64] first query of every chunk
-  int* s_cp0 = s_qrng + 64;                                            // [64] bin position of column 0 of every chunk
-  float* s_db = reinterpret_cast<float*>(s_cp0 + 64);                 // [4 quarters][32 columns][DBS] dB of a chunk
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
   const unsigned long long ncl = ce - cb;
   if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
-  const int nq = P->nq, nb = P->nb;
-  const int n_chunks = P->tc_nch;
+  const int nq = (NQC > 0) ? NQC : P->nq;
+  const int n_chunks = (nq + TC_QC - 1) / TC_QC;
   const unsigned long long n_tiles = (ncl + TC_M - 1) / TC_M;
   // normalisation max(P): the plan's own search, or the all-reduced value of a sharded run
   const double pmax = gmax_dev ? *gmax_dev : P->pmax_raw;
   if (gmax_dev && blockIdx.x == 0 && threadIdx.x == 0) P->pmax_raw = pmax;
+  const double inv_d = 1.0 / sqrt(pmax);
 
   // barriers: [0,1] a_full, [2,3] a_empty, [4,5] b_full, [6,7] b_empty, [8,9] t_full, [10,11] t_empty
   const uint32_t bar0 = smem_u32(&s_bar[0]);
   auto BAR = [&](int i) { return bar0 + (uint32_t)(i * 8); };
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(0 + i), EW * 32); mbar_init(BAR(2 + i), 1);
+      mbar_init(BAR(0 + i), TC_EW * 32); mbar_init(BAR(2 + i), 1);
       mbar_init(BAR(4 + i), 1); mbar_init(BAR(6 + i), 1);
-      mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), EW * 32);
+      mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), TC_EW * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  if (warp == EW) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(S::TMEM_COLS));
+  if (warp == TC_EW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < nq; i += S::THREADS) { s_aq[i] = t.aq[i]; s_qpos[i] = t.qpos[i]; }
-  if (tid <= n_chunks && tid < 64) {   // queries [s_qrng[ch], s_qrng[ch+1]) have both brackets inside chunk ch
-    s_qrng[tid] = P->tc_q0[tid];
-    s_cp0[tid] = P->tc_p0[tid];
-  }
-  if (tid < 2 * TC_HALF) s_ws[tid] = (float)((double)t.win[tid] / sqrt(pmax));
+  for (int i = tid; i < MAX_NQ; i += TC_THREADS) s_aq[i] = (i < nq) ? t.aq[i] : 0.f;
+  if (tid < 2 * TC_HALF) s_ws[tid] = (float)((double)t.win[tid] * inv_d);
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < EW) {
+  if (warp < TC_EW) {
     // ====== epilogue warps: lane quarter qd = warp & 3 (TMEM lanes 32*qd..), sub-warp sw = warp >> 2 ======
     const int qd = warp & 3, sw = warp >> 2;
     const int m = qd * 32 + lane;                         // row of the tile = spectrogram column = TMEM lane
-    const uint32_t a_aq = smem_u32(s_aq), a_qpos = smem_u32(s_qpos);
-    const uint32_t a_db = smem_u32(s_db) + (uint32_t)(qd * 32 * DBS * 4);      // dB rows of this quarter's 32 columns
-    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const float inv = (float)(1.0 / sqrt(pmax));
-    // the only positions without the one-sided doubling: bin 0 (if planned) and the Nyquist bin
-    const int sp0 = (t.bins[0] == 0) ? 0 : -1;
-    const int sp1 = ((unsigned long long)t.bins[nb - 1] == P->nfft / 2) ? nb - 1 : -1;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(sw * 32);
+    const uint32_t a_aq = smem_u32(s_aq) + (uint32_t)(sw * 16 * 4);            // weights of this warp's 16 queries
+    const uint32_t a_stq = smem_u32(s_stg) + (uint32_t)(qd * TC_SQ * 4);       // this quarter's staging rows
+    const uint32_t a_st_w = a_stq + (uint32_t)((lane * TC_SROW + sw * 16) * 4);        // store: own column, own 16 queries
+    const uint32_t a_st_r = a_stq + (uint32_t)((sw * 8 * TC_SROW + 2 * lane) * 4);     // load: 8 columns, 2 queries per lane
 
-    // A operands of one column: mean removed in float64, windowed, folded even/odd, split hi/lo.  The SW warps of a
-    // quarter share the work: this warp writes 4/SW of the four matrices Ehi | Elo | Ohi | Olo.
+    // A operands of one column: a TF32-exact mean estimate removed in float64, windowed, folded even/odd, split
+    // hi/lo and laid out along K as [hi | hi | lo | M M].  The four warps of a quarter share the work: warp sw
+    // writes K slots 16*(sw&1).. of E (sw < 2) or O.
     auto build_a = [&](unsigned long long tile, int buf) {
       unsigned long long col = cb + tile * TC_M + m;
       if (col >= ce) col = ce - 1;
@@ -297,175 +289,135 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
 #pragma unroll
       for (int n = 0; n < 2 * TC_HALF; ++n) { xd[n] = __ldg(xs + n); mean_d += xd[n]; }
       mean_d *= (1.0 / (2 * TC_HALF));
-      const float mean = (float)mean_d;        // the DC tap carries the float32 mean; its rounding error joins the residual
+      const float M = tf32_rna((float)(mean_d * inv_d));   // DC slot value; mu = M / inv is what the residual removes
+      const double mu = (double)M * sqrt(pmax);
       float yv[2 * TC_HALF];
 #pragma unroll
-      for (int n = 0; n < 2 * TC_HALF; ++n) yv[n] = s_ws[n] * (float)(xd[n] - (double)mean);
+      for (int n = 0; n < 2 * TC_HALF; ++n) yv[n] = s_ws[n] * (float)(xd[n] - mu);
+      const bool even = sw < 2;
+      float hi[TC_HALF], lo[TC_HALF];
 #pragma unroll
-      for (int mi = 0; mi < 4 / SW; ++mi) {
-        const int mat = sw * (4 / SW) + mi;                // 0 Ehi, 1 Elo, 2 Ohi, 3 Olo
-        const bool even = mat < 2, lo = (mat & 1) != 0;
-        float v[TC_KP];
-#pragma unroll
-        for (int k = 0; k < TC_HALF; ++k)
-          v[k] = even ? (yv[TC_HALF - 1 - k] + yv[TC_HALF + k]) : (yv[TC_HALF - 1 - k] - yv[TC_HALF + k]);
-        v[TC_HALF] = even ? mean * inv : 0.f;               // DC tap: multiplies the tabulated window response
-#pragma unroll
-        for (int k = TC_HALF + 1; k < TC_KP; ++k) v[k] = 0.f;
-        float* rowp = sA + buf * (4 * TC_A_MAT_BYTES / 4) + mat * (TC_A_MAT_BYTES / 4) + (m >> 3) * (TC_KP * 8) + (m & 7) * 4;
-#pragma unroll
-        for (int kc = 0; kc < TC_KP / 4; ++kc) {
-          float4 o4;
-          float* op = &o4.x;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float hi = tf32_rna(v[4 * kc + j]);
-            op[j] = lo ? tf32_rna(v[4 * kc + j] - hi) : hi;
-          }
-          *reinterpret_cast<float4*>(rowp + kc * 32) = o4;
-        }
+      for (int k = 0; k < TC_HALF; ++k) {
+        const float v = even ? (yv[TC_HALF - 1 - k] + yv[TC_HALF + k]) : (yv[TC_HALF - 1 - k] - yv[TC_HALF + k]);
+        hi[k] = tf32_rna(v);
+        lo[k] = tf32_rna(v - hi[k]);
+      }
+      const float dc = even ? M : 0.f;
+      float* rowp = sA + buf * (TC_A_BYTES / 4) + (even ? 0 : TC_A_MAT_BYTES / 4) + (m >> 3) * (TC_K * 8) + (m & 7) * 4;
+      if ((sw & 1) == 0) {        // slots 0..15: hi[0..9], hi[0..5]
+        *reinterpret_cast<float4*>(rowp + 0 * 32) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(rowp + 1 * 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<float4*>(rowp + 2 * 32) = make_float4(hi[8], hi[9], hi[0], hi[1]);
+        *reinterpret_cast<float4*>(rowp + 3 * 32) = make_float4(hi[2], hi[3], hi[4], hi[5]);
+      } else {                    // slots 16..31: hi[6..9], lo[0..9], dc, dc
+        *reinterpret_cast<float4*>(rowp + 4 * 32) = make_float4(hi[6], hi[7], hi[8], hi[9]);
+        *reinterpret_cast<float4*>(rowp + 5 * 32) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(rowp + 6 * 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+        *reinterpret_cast<float4*>(rowp + 7 * 32) = make_float4(lo[8], lo[9], dc, dc);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
       mbar_arrive(BAR(0 + buf));
     };
 
+    // the finished chunk still in the staging rows: its 8 columns x 64 queries leave as 256-byte rows while the
+    // next chunk's lg2 phase runs
+    float* pend_ptr = nullptr;      // out + this warp's first column row + chunk's first query + 2*lane
+    int pend_cols = 0, pend_q = 0;  // valid columns among the warp's 8; first query of this lane's pair
+    uint32_t pend_addr = 0;
+    auto flush_col = [&](int j) {
+      if (LAYOUT != 0 || j >= pend_cols) return;
+      const float2 v = lds64(pend_addr + (uint32_t)(j * TC_SROW * 4));
+      if (dbg_mode == 2) { if (v.x == 123.456f) pend_ptr[0] = v.y; return; }
+      if (NQC > 0) {
+        *reinterpret_cast<float2*>(pend_ptr + (size_t)j * NQC) = v;
+      } else {
+        float* p = pend_ptr + (size_t)j * nq;
+        if (pend_q < nq) p[0] = v.x;
+        if (pend_q + 1 < nq) p[1] = v.y;
+      }
+    };
+
+    // |S|^2 -> lg2 of the (lower, upper) pairs of 8 queries, interp1 in registers, dB; every other pair of queries
+    // also moves one staged column of the previous chunk to global memory (columns jf .. jf+3)
+    const float2 kk = make_float2(K_DB, K_DB);
+    auto half_chunk = [&](const float (&re)[16], const float (&im)[16], uint32_t a_w, float* o, int jf) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 ra = make_float2(re[4 * j], re[4 * j + 1]), ia = make_float2(im[4 * j], im[4 * j + 1]);
+        const float2 rb = make_float2(re[4 * j + 2], re[4 * j + 3]), ib = make_float2(im[4 * j + 2], im[4 * j + 3]);
+        const float2 pa = fma2(ra, ra, mul2(ia, ia)), pb = fma2(rb, rb, mul2(ib, ib));   // (lower, upper) of queries 2j, 2j+1
+        const float2 l_lo = make_float2(lg2_approx(pa.x), lg2_approx(pb.x));
+        const float2 l_hi = make_float2(lg2_approx(pa.y), lg2_approx(pb.y));
+        const float2 a2 = lds64(a_w + (uint32_t)(j * 8));
+        const float2 o2 = mul2(kk, fma2(a2, sub2(l_hi, l_lo), l_lo));
+        o[2 * j] = o2.x; o[2 * j + 1] = o2.y;
+        flush_col(jf + j);
+      }
+    };
+    const bool skip_math = (dbg_mode == 1 || dbg_mode == 4);
+    float reA[16], imA[16], reB[16], imB[16];              // accumulator halves: one in use, one in flight
+
     unsigned long long it = 0;                            // local tile counter
     if (blockIdx.x < n_tiles) build_a(blockIdx.x, 0);
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const unsigned long long next = tile + gridDim.x;
-      if (ABUF == 2 && next < n_tiles) {                  // A of the next tile while this tile's chunks are in flight
+      if (next < n_tiles) {                               // A of the next tile while this tile's chunks are in flight
         const int nbuf = (int)((it + 1) & 1);
         mbar_wait(BAR(2 + nbuf), (uint32_t)((((it + 1) >> 1) & 1) ^ 1));
         build_a(next, nbuf);
       }
       const unsigned long long tile_col0 = cb + tile * TC_M;
-      const unsigned long long warp_col0 = tile_col0 + (unsigned long long)qd * 32;
-      const int ncols_valid = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 32ull ? (ce - warp_col0) : 32ull);
-      float* out_warp = out + (warp_col0 - cb) * (unsigned long long)nq;      // time-major rows of this quarter's columns
+      const unsigned long long warp_col0 = tile_col0 + (unsigned long long)(qd * 32 + sw * 8);   // first of the warp's 8 store columns
+      const int wcols = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 8ull ? (ce - warp_col0) : 8ull);
       const bool col_ok = (tile_col0 + m) < ce;
       for (int ch = 0; ch < n_chunks; ++ch) {
         const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
         const int ts = (int)(cseq & 1);
-        const int gi = (sw + ch) % SW;                      // 32-bin group of this chunk converted to dB by this warp
-        const int pos_c0 = s_cp0[ch];                       // bin position of chunk column 0
+        const uint32_t c0 = t_lane + (uint32_t)(ts * 2 * TC_N);
         mbar_wait(BAR(8 + ts), (uint32_t)((cseq >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-          float re[32], im[32];
-          const uint32_t c0 = (uint32_t)(ts * 2 * BN + gi * 32);
-          float a16[16];
-          tmem_ld16(t_lane + c0, a16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) re[j] = a16[j];
-          tmem_ld16(t_lane + c0 + 16, a16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) re[16 + j] = a16[j];
-          tmem_ld16(t_lane + c0 + BN, a16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) im[j] = a16[j];
-          tmem_ld16(t_lane + c0 + BN + 16, a16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) im[16 + j] = a16[j];
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(BAR(10 + ts));                        // accumulators are in registers: TMEM stage back to the MMA warp
-          if (dbg_mode == 1) { if (re[0] + im[31] == 123.456f) out[0] = 1.f; continue; }
-          // |S|^2 -> dB of 32 bins (independent chains, two bins per packed FMUL2 / FFMA2), one-sided doubling for
-          // all bins; the (at most two) un-doubled positions are corrected below
-          // even positions of the chunk go to the first plane of the row, odd ones to the plane at DB_OFF
-          const uint32_t a_row = a_db + (uint32_t)((lane * DBS + gi * 16) * 4);
-          const float2 kk = make_float2(K_DB, K_DB);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float2 ra = make_float2(re[j], re[j + 1]), ia = make_float2(im[j], im[j + 1]);
-            const float2 rb = make_float2(re[j + 2], re[j + 3]), ib = make_float2(im[j + 2], im[j + 3]);
-            const float2 pa = fma2(ra, ra, mul2(ia, ia)), pb = fma2(rb, rb, mul2(ib, ib));
-            const float2 le = make_float2(lg2_approx(pa.x), lg2_approx(pb.x));   // positions j, j+2
-            const float2 lo = make_float2(lg2_approx(pa.y), lg2_approx(pb.y));   // positions j+1, j+3
-            sts64(a_row + (uint32_t)(j * 2), fma2(kk, le, kk));
-            sts64(a_row + (uint32_t)(DB_OFF * 4 + j * 2), fma2(kk, lo, kk));
-          }
-          const int p_lo = pos_c0 + gi * 32;
-          if ((sp0 >= p_lo && sp0 < p_lo + 32) || (sp1 >= p_lo && sp1 < p_lo + 32)) {
-            __syncwarp();
-            const int sp = (sp0 >= p_lo && sp0 < p_lo + 32) ? sp0 : sp1;
-            const int rp = sp - pos_c0;
-            const uint32_t aa = a_db + (uint32_t)((lane * DBS + (rp >> 1) + (rp & 1) * DB_OFF) * 4);
-            sts32(aa, lds32(aa) - K_DB);
-          }
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(SW * 32) : "memory");   // the quarter's dB rows are complete
-        // ---- interp1 onto the log-frequency axis: queries whose bracket lies in this chunk, in blocks of 32 ----
-        const int Qa = s_qrng[ch], Qb = (dbg_mode == 2) ? s_qrng[ch] : s_qrng[ch + 1];
+        tmem_ld16(c0, reA);
+        tmem_ld16(c0 + TC_N, imA);
+        tmem_ld16(c0 + 16, reB);
+        tmem_ld16(c0 + TC_N + 16, imB);
+        tmem_wait_ld(reA, imA);
+        tmem_wait_ld(reB, imB);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(BAR(10 + ts));                        // accumulators are in registers: TMEM stage back to the MMA warp
+        if (skip_math) { if (reA[0] + imB[15] == 123.456f) out[0] = 1.f; continue; }
+        const uint32_t a_w = a_aq + (uint32_t)(ch * TC_QC * 4);
+        float o[16];
+        half_chunk(reA, imA, a_w, o, 0);
+        half_chunk(reB, imB, a_w + 32u, o + 8, 4);
         if (LAYOUT == 0) {
-          // lanes = 32 consecutive queries (coalesced 128-byte rows, no staging); the SW warps of a quarter split
-          // its 32 columns, so the work is balanced whatever the number of query blocks
-          const int c_lo = sw * CW;
-          for (int b = Qa >> 5; b * 32 < Qb; ++b) {
-            const int q = b * 32 + lane;
-            const bool ok = q >= Qa && q < Qb;
-            const int jl = ok ? __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0 : 0;
-            const float a = lds32(a_aq + 4 * q);
-            const uint32_t ad = a_db + (uint32_t)((c_lo * DBS + (jl >> 1) + (jl & 1) * DB_OFF) * 4);           // lower bracket
-            const uint32_t au = a_db + (uint32_t)((c_lo * DBS + ((jl + 1) >> 1) + ((jl + 1) & 1) * DB_OFF) * 4);  // upper bracket
-            if (NQC > 0 && ncols_valid == 32) {
-              float* ptr = out_warp + (unsigned long long)c_lo * NQC + q;
+          const uint32_t aw = a_st_w + (uint32_t)(ts * TC_SBUF * 4);
 #pragma unroll
-              for (int c8 = 0; c8 < CW; c8 += 8) {
-                float lo[8], hi[8];
+          for (int i = 0; i < 4; ++i) sts128(aw + (uint32_t)(i * 16), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(128) : "memory");   // the quarter's 32 x 64 outputs are staged
+          pend_addr = a_st_r + (uint32_t)(ts * TC_SBUF * 4);
+          pend_q = ch * TC_QC + 2 * lane;
+          pend_ptr = out + (warp_col0 - cb) * (unsigned long long)nq + pend_q;
+          pend_cols = wcols;
+        } else if (col_ok) {
+          // frequency-major: lanes = consecutive columns, coalesced 128-byte rows straight from registers
+          float* p = out + (unsigned long long)(ch * TC_QC + sw * 16) * ld_cols + (tile_col0 + m - cb);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  lo[c] = lds32(ad + (uint32_t)((c8 + c) * DBS * 4));
-                  hi[c] = lds32(au + (uint32_t)((c8 + c) * DBS * 4));
-                }
-                if (ok && dbg_mode != 3) {
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) ptr[(c8 + c) * NQC] = fmaf(a, hi[c] - lo[c], lo[c]);
-                } else if (dbg_mode == 3) {
-                  float acc = 0.f;
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) acc += fmaf(a, hi[c] - lo[c], lo[c]);
-                  if (acc == 123.456f) ptr[0] = acc;
-                }
-              }
-            } else if (ok) {
-              float* ptr = out_warp + (unsigned long long)c_lo * nq + q;
-              for (int c = 0; c < CW && c_lo + c < ncols_valid; ++c) {
-                const float lo = lds32(ad + (uint32_t)(c * DBS * 4)), hi = lds32(au + (uint32_t)(c * DBS * 4));
-                ptr[(unsigned long long)c * nq] = fmaf(a, hi - lo, lo);
-              }
-            }
-          }
-        } else {
-          // lanes = columns: coalesced rows of the frequency-major layout; query blocks are dealt to the SW warps
-          for (int b = (Qa >> 5) + ((sw + SW * 64 - (Qa >> 5) % SW - ch % SW) % SW); b * 32 < Qb; b += SW) {
-            const int q0 = max(Qa, b * 32), q1 = min(Qb, b * 32 + 32);
-            const uint32_t ad = a_db + (uint32_t)(lane * DBS * 4);
-            for (int q = q0; q < q1; ++q) {
-              const int jq = __float_as_int(lds32(a_qpos + 4 * q)) - pos_c0;
-              const float a = lds32(a_aq + 4 * q);
-              const float lo = lds32(ad + (uint32_t)(((jq >> 1) + (jq & 1) * DB_OFF) * 4));
-              const float hi = lds32(ad + (uint32_t)((((jq + 1) >> 1) + ((jq + 1) & 1) * DB_OFF) * 4));
-              if (col_ok) out[(unsigned long long)q * ld_cols + (tile_col0 + m - cb)] = fmaf(a, hi - lo, lo);
-            }
-          }
+          for (int i = 0; i < 16; ++i)
+            if (NQC > 0 || ch * TC_QC + sw * 16 + i < nq) p[(unsigned long long)i * ld_cols] = o[i];
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(SW * 32) : "memory");   // dB rows may be overwritten by the next chunk
-      }
-      if (ABUF == 1 && next < n_tiles) {                  // single A buffer: rebuild once this tile's MMAs have retired
-        mbar_wait(BAR(2), (uint32_t)(it & 1));
-        build_a(next, 0);
       }
     }
-  } else if (warp == EW) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) flush_col(j);
+  } else if (warp == TC_EW) {
     // ===================== MMA issuer: one thread drives the tensor core =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
       unsigned long long it = 0;
       for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int abuf = (ABUF == 2) ? (int)(it & 1) : 0;
-        mbar_wait(BAR(0 + abuf), (uint32_t)(((ABUF == 2) ? (it >> 1) : it) & 1));
-        const uint32_t aA = smem_u32(sA) + (uint32_t)(abuf * 4 * TC_A_MAT_BYTES);
+        const int abuf = (int)(it & 1);
+        mbar_wait(BAR(0 + abuf), (uint32_t)((it >> 1) & 1));
+        const uint32_t aA = smem_u32(sA) + (uint32_t)(abuf * TC_A_BYTES);
         for (int ch = 0; ch < n_chunks; ++ch) {
           const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
           const int st = (int)(cseq & 1);
@@ -473,19 +425,14 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           mbar_wait(BAR(4 + st), par);               // B tile landed
           mbar_wait(BAR(10 + st), par ^ 1);          // TMEM stage drained (passes immediately the first two times)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t aB = smem_u32(sB) + (uint32_t)(st * S::B_BYTES);
+          const uint32_t aB = smem_u32(sB) + (uint32_t)(st * TC_B_BYTES);
 #pragma unroll
           for (int part = 0; part < 2; ++part) {          // 0: Re = E * C^T, 1: Im = O * S^T
-            const uint32_t d = tmem_base + (uint32_t)(st * 2 * BN + part * BN);
-            const uint32_t a_hi = aA + (uint32_t)((2 * part) * TC_A_MAT_BYTES), a_lo = a_hi + TC_A_MAT_BYTES;
-            const uint32_t b_hi = aB + (uint32_t)((2 * part) * S::B_MAT_BYTES), b_lo = b_hi + S::B_MAT_BYTES;
+            const uint32_t d = tmem_base + (uint32_t)(st * 2 * TC_N + part * TC_N);
+            const uint32_t a = aA + (uint32_t)(part * TC_A_MAT_BYTES), b = aB + (uint32_t)(part * TC_B_MAT_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < TC_KP / 8; ++ks) {
-              const uint32_t o = (uint32_t)(ks * 256);
-              umma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), idesc, ks > 0);
-              umma_tf32(d, make_desc(a_hi + o), make_desc(b_lo + o), idesc, 1u);
-              umma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), idesc, 1u);
-            }
+            for (int ks = 0; ks < TC_K / 8; ++ks)
+              umma_tf32(d, make_desc(a + (uint32_t)(ks * 256)), make_desc(b + (uint32_t)(ks * 256)), idesc, ks > 0);
           }
           umma_commit(BAR(6 + st));                    // B stage consumed
           umma_commit(BAR(8 + st));                    // accumulators ready
@@ -503,8 +450,9 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
           const int st = (int)(cseq & 1);
           mbar_wait(BAR(6 + st), (uint32_t)(((cseq >> 1) & 1) ^ 1));
-          mbar_expect_tx(BAR(4 + st), S::B_BYTES);
-          bulk_g2s(smem_u32(sB) + (uint32_t)(st * S::B_BYTES), tcB + (size_t)ch * (S::B_BYTES / 4), S::B_BYTES, BAR(4 + st));
+          if (dbg_mode >= 4 && it > 0) { mbar_arrive(BAR(4 + st)); continue; }   // timing experiment: B tiles not reloaded
+          mbar_expect_tx(BAR(4 + st), TC_B_BYTES);
+          bulk_g2s(smem_u32(sB) + (uint32_t)(st * TC_B_BYTES), tcB + (size_t)ch * (TC_B_BYTES / 4), TC_B_BYTES, BAR(4 + st));
         }
       }
     }
@@ -512,35 +460,28 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS));
-}
-
-static int tc_shape_bn() {
-  static int bn = 0;
-  if (!bn) { const char* v = getenv("FMCW_TC_BN"); bn = (v && atoi(v) == 64) ? 64 : 128; }
-  return bn;
+  if (warp == TC_EW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
 }
 
 size_t stft_tc_table_bytes(int nb_max) {
-  // at most one chunk per block of 32 queries, BN <= 128 rows each, four matrices of TC_KP floats per row
   (void)nb_max;
-  return (size_t)MAX_CHUNKS * 128 * TC_KP * 4 * 4;
+  return (size_t)(MAX_NQ / TC_QC) * TC_B_BYTES;      // one (C | S) pair per chunk of 64 queries
 }
 
 cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float* tcB, int nb_max, cudaStream_t st,
                                    int spec_mode) {
   (void)nb_max;
-  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, tc_shape_bn(), spec_mode);
+  stft_tc_prepare_kernel<<<64, 256, 0, st>>>(t, g, tcB, spec_mode);
   return cudaGetLastError();
 }
 
-template <int L, int Q, class S>
-static cudaError_t launch_tc_shape(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
-                                   unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, cudaStream_t st,
-                                   const double* gmax_dev, int sms, int dbg) {
-  cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<L, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM);
+template <int L, int Q>
+static cudaError_t launch_tc(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
+                             unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, cudaStream_t st,
+                             const double* gmax_dev, int sms, int dbg) {
+  cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<L, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   if (e != cudaSuccess) return e;
-  stft_tc_kernel<L, Q, S><<<sms * S::CTAS, S::THREADS, S::SMEM, st>>>(t, g, x, out, tcB, capacity_cols, ld_cols, d_err, dbg, gmax_dev);
+  stft_tc_kernel<L, Q><<<sms, TC_THREADS, TC_SMEM, st>>>(t, g, x, out, tcB, capacity_cols, ld_cols, d_err, dbg, gmax_dev);
   return cudaGetLastError();
 }
 
@@ -551,15 +492,11 @@ cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const si
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   static int dbg = -1;
   if (dbg < 0) { const char* v = getenv("FMCW_TC_DEBUG"); dbg = v ? atoi(v) : 0; }
-  using S1 = TcShape<128, 16, 1>;
-  using S2 = TcShape<64, 8, 2>;
 #define FMCW_TC_ARGS t, g, x, out, tcB, capacity_cols, ld_cols, d_err, st, gmax_dev, sms, dbg
-  if (tc_shape_bn() == 128) {
-    if (layout != 0) return launch_tc_shape<1, 0, S1>(FMCW_TC_ARGS);
-    return g.nq == 1024 ? launch_tc_shape<0, 1024, S1>(FMCW_TC_ARGS) : launch_tc_shape<0, 0, S1>(FMCW_TC_ARGS);
-  }
-  if (layout != 0) return launch_tc_shape<1, 0, S2>(FMCW_TC_ARGS);
-  return g.nq == 1024 ? launch_tc_shape<0, 1024, S2>(FMCW_TC_ARGS) : launch_tc_shape<0, 0, S2>(FMCW_TC_ARGS);
+  if (layout != 0) return launch_tc<1, 0>(FMCW_TC_ARGS);
+  // the fast path stores 64-bit pairs: 1,024 queries and an 8-byte aligned spectrogram
+  if (g.nq == 1024 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) return launch_tc<0, 1024>(FMCW_TC_ARGS);
+  return launch_tc<0, 0>(FMCW_TC_ARGS);
 #undef FMCW_TC_ARGS
 }
 
