@@ -53,7 +53,7 @@ constexpr int TC_OFF_B = 2 * TC_A_BYTES;
 constexpr int TC_OFF_STG = TC_OFF_B + 2 * TC_B_BYTES;
 constexpr int TC_OFF_AQ = TC_OFF_STG + 2 * TC_SBUF * 4;
 constexpr int TC_OFF_BAR = TC_OFF_AQ + (MAX_NQ + 32) * 4;
-constexpr int TC_SMEM = TC_OFF_BAR + 16 * 8 + 16;
+constexpr int TC_SMEM = TC_OFF_BAR + 24 * 8 + 16;
 static_assert(MAX_NQ % TC_QC == 0, "query table is padded to whole chunks");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -231,7 +231,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   float* s_aq = reinterpret_cast<float*>(smem + TC_OFF_AQ);            // [MAX_NQ] interp1 weights (zero padded)
   float* s_ws = s_aq + MAX_NQ;                                         // [32] normalised window
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 24);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
@@ -245,15 +245,17 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   if (gmax_dev && blockIdx.x == 0 && threadIdx.x == 0) P->pmax_raw = pmax;
   const double inv_d = 1.0 / sqrt(pmax);
 
-  // barriers: [0,1] a_full, [2,3] a_empty, [4,5] b_full, [6,7] b_empty, [8,9] t_full, [10,11] t_empty
+  // barriers: [0,1] a_full, [2,3] a_empty, [4,5] b_full, [6,7] b_empty, [8,9] t_full, [10,11] t_empty,
+  // [12 + 2*quarter + buffer] staging rows of a quarter complete (one arrival per warp)
   const uint32_t bar0 = smem_u32(&s_bar[0]);
   auto BAR = [&](int i) { return bar0 + (uint32_t)(i * 8); };
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(0 + i), TC_EW * 32); mbar_init(BAR(2 + i), 1);
+      mbar_init(BAR(0 + i), TC_EW); mbar_init(BAR(2 + i), 1);
       mbar_init(BAR(4 + i), 1); mbar_init(BAR(6 + i), 1);
-      mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), TC_EW * 32);
+      mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), TC_EW);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(BAR(12 + i), 4);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == TC_EW) {
@@ -316,24 +318,27 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         *reinterpret_cast<float4*>(rowp + 7 * 32) = make_float4(lo[8], lo[9], dc, dc);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
-      mbar_arrive(BAR(0 + buf));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(0 + buf));              // one arrival per warp
     };
 
     // the finished chunk still in the staging rows: its 8 columns x 64 queries leave as 256-byte rows while the
     // next chunk's lg2 phase runs
-    float* pend_ptr = nullptr;      // out + this warp's first column row + chunk's first query + 2*lane
+    float* pend_ptr = out;          // out + this warp's first column row + chunk's first query + 2*lane
     int pend_cols = 0, pend_q = 0;  // valid columns among the warp's 8; first query of this lane's pair
-    uint32_t pend_addr = 0;
+    uint32_t pend_addr = 0, pend_bar = 0, pend_par = 0;
+    bool pending = false;
     auto flush_col = [&](int j) {
-      if (LAYOUT != 0 || j >= pend_cols) return;
+      if (LAYOUT != 0 || !pending) return;
+      if (j == 0) mbar_wait(pend_bar, pend_par);            // the other three warps of the quarter have staged their queries
       const float2 v = lds64(pend_addr + (uint32_t)(j * TC_SROW * 4));
-      if (dbg_mode == 2) { if (v.x == 123.456f) pend_ptr[0] = v.y; return; }
+      const bool ok = j < pend_cols;
       if (NQC > 0) {
-        *reinterpret_cast<float2*>(pend_ptr + (size_t)j * NQC) = v;
+        if (ok) *reinterpret_cast<float2*>(pend_ptr + (size_t)j * NQC) = v;
       } else {
         float* p = pend_ptr + (size_t)j * nq;
-        if (pend_q < nq) p[0] = v.x;
-        if (pend_q + 1 < nq) p[1] = v.y;
+        if (ok && pend_q < nq) p[0] = v.x;
+        if (ok && pend_q + 1 < nq) p[1] = v.y;
       }
     };
 
@@ -354,7 +359,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         flush_col(jf + j);
       }
     };
-    const bool skip_math = (dbg_mode == 1 || dbg_mode == 4);
+    const bool skip_math = (dbg_mode == 1);
     float reA[16], imA[16], reB[16], imB[16];              // accumulator halves: one in use, one in flight
 
     unsigned long long it = 0;                            // local tile counter
@@ -383,7 +388,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         tmem_wait_ld(reA, imA);
         tmem_wait_ld(reB, imB);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(BAR(10 + ts));                        // accumulators are in registers: TMEM stage back to the MMA warp
+        if (lane == 0) mbar_arrive(BAR(10 + ts));         // (warp-collective loads are complete) TMEM stage back to the MMA warp
         if (skip_math) { if (reA[0] + imB[15] == 123.456f) out[0] = 1.f; continue; }
         const uint32_t a_w = a_aq + (uint32_t)(ch * TC_QC * 4);
         float o[16];
@@ -393,7 +398,11 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           const uint32_t aw = a_st_w + (uint32_t)(ts * TC_SBUF * 4);
 #pragma unroll
           for (int i = 0; i < 4; ++i) sts128(aw + (uint32_t)(i * 16), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "n"(128) : "memory");   // the quarter's 32 x 64 outputs are staged
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(12 + 2 * qd + ts));  // this warp's 16 queries of the quarter's 32 x 64 outputs are staged
+          pending = true;
+          pend_bar = BAR(12 + 2 * qd + ts);
+          pend_par = (uint32_t)((cseq >> 1) & 1);
           pend_addr = a_st_r + (uint32_t)(ts * TC_SBUF * 4);
           pend_q = ch * TC_QC + 2 * lane;
           pend_ptr = out + (warp_col0 - cb) * (unsigned long long)nq + pend_q;
@@ -450,7 +459,6 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
           const int st = (int)(cseq & 1);
           mbar_wait(BAR(6 + st), (uint32_t)(((cseq >> 1) & 1) ^ 1));
-          if (dbg_mode >= 4 && it > 0) { mbar_arrive(BAR(4 + st)); continue; }   // timing experiment: B tiles not reloaded
           mbar_expect_tx(BAR(4 + st), TC_B_BYTES);
           bulk_g2s(smem_u32(sB) + (uint32_t)(st * TC_B_BYTES), tcB + (size_t)ch * (TC_B_BYTES / 4), TC_B_BYTES, BAR(4 + st));
         }
