@@ -142,6 +142,20 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 }
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
+// volatile: keeps its place among the (volatile) shared-memory and global accesses of the epilogue loop, so the
+// MUFU work stays spread over the loop instead of being bunched by the scheduler
+__device__ __forceinline__ float lg2_pinned(float x) {
+  float y;
+  asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void stg64_if(float* p, float2 v, bool ok) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %3, 0;\n@q st.global.v2.f32 [%0], {%1, %2};\n}"
+               ::"l"(p), "f"(v.x), "f"(v.y), "r"((int)ok) : "memory");
+}
+__device__ __forceinline__ void stg32_if(float* p, float v, bool ok) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q st.global.f32 [%0], %1;\n}" ::"l"(p), "f"(v), "r"((int)ok) : "memory");
+}
 __device__ __forceinline__ float2 lds64(uint32_t a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
@@ -325,25 +339,30 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
     // the finished chunk still in the staging rows: its 8 columns x 64 queries leave as 256-byte rows while the
     // next chunk's lg2 phase runs
     float* pend_ptr = out;          // out + this warp's first column row + chunk's first query + 2*lane
-    int pend_cols = 0, pend_q = 0;  // valid columns among the warp's 8; first query of this lane's pair
-    uint32_t pend_addr = 0, pend_bar = 0, pend_par = 0;
+    int pend_cols = 0, pend_q = 0;  // valid columns among the warp's 8 (0: nothing staged yet); first query of this lane's pair
+    uint32_t pend_addr = a_st_r, pend_bar = 0, pend_par = 0;
     bool pending = false;
-    auto flush_col = [&](int j) {
-      if (LAYOUT != 0 || !pending) return;
-      if (j == 0) mbar_wait(pend_bar, pend_par);            // the other three warps of the quarter have staged their queries
-      const float2 v = lds64(pend_addr + (uint32_t)(j * TC_SROW * 4));
+    float2 pend_v = make_float2(0.f, 0.f);
+    auto flush_begin = [&]() {      // the other three warps of the quarter have staged their queries; first row in flight
+      if (LAYOUT != 0) return;
+      if (pending) mbar_wait(pend_bar, pend_par);
+      pend_v = lds64(pend_addr);
+    };
+    auto flush_col = [&](int j) {   // store row j (loaded one step earlier), load row j + 1
+      if (LAYOUT != 0) return;
       const bool ok = j < pend_cols;
       if (NQC > 0) {
-        if (ok) *reinterpret_cast<float2*>(pend_ptr + (size_t)j * NQC) = v;
+        stg64_if(pend_ptr + (size_t)j * NQC, pend_v, ok);
       } else {
         float* p = pend_ptr + (size_t)j * nq;
-        if (ok && pend_q < nq) p[0] = v.x;
-        if (ok && pend_q + 1 < nq) p[1] = v.y;
+        stg32_if(p, pend_v.x, ok && pend_q < nq);
+        stg32_if(p + 1, pend_v.y, ok && pend_q + 1 < nq);
       }
+      if (j < 7) pend_v = lds64(pend_addr + (uint32_t)((j + 1) * TC_SROW * 4));
     };
 
-    // |S|^2 -> lg2 of the (lower, upper) pairs of 8 queries, interp1 in registers, dB; every other pair of queries
-    // also moves one staged column of the previous chunk to global memory (columns jf .. jf+3)
+    // |S|^2 -> lg2 of the (lower, upper) pairs of 8 queries, interp1 in registers, dB; every pair of queries also
+    // moves one staged row of the previous chunk to global memory (rows jf .. jf+3)
     const float2 kk = make_float2(K_DB, K_DB);
     auto half_chunk = [&](const float (&re)[16], const float (&im)[16], uint32_t a_w, float* o, int jf) {
 #pragma unroll
@@ -351,12 +370,12 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         const float2 ra = make_float2(re[4 * j], re[4 * j + 1]), ia = make_float2(im[4 * j], im[4 * j + 1]);
         const float2 rb = make_float2(re[4 * j + 2], re[4 * j + 3]), ib = make_float2(im[4 * j + 2], im[4 * j + 3]);
         const float2 pa = fma2(ra, ra, mul2(ia, ia)), pb = fma2(rb, rb, mul2(ib, ib));   // (lower, upper) of queries 2j, 2j+1
-        const float2 l_lo = make_float2(lg2_approx(pa.x), lg2_approx(pb.x));
-        const float2 l_hi = make_float2(lg2_approx(pa.y), lg2_approx(pb.y));
+        flush_col(jf + j);
+        const float2 l_lo = make_float2(lg2_pinned(pa.x), lg2_pinned(pb.x));
+        const float2 l_hi = make_float2(lg2_pinned(pa.y), lg2_pinned(pb.y));
         const float2 a2 = lds64(a_w + (uint32_t)(j * 8));
         const float2 o2 = mul2(kk, fma2(a2, sub2(l_hi, l_lo), l_lo));
         o[2 * j] = o2.x; o[2 * j + 1] = o2.y;
-        flush_col(jf + j);
       }
     };
     const bool skip_math = (dbg_mode == 1);
@@ -392,6 +411,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         if (skip_math) { if (reA[0] + imB[15] == 123.456f) out[0] = 1.f; continue; }
         const uint32_t a_w = a_aq + (uint32_t)(ch * TC_QC * 4);
         float o[16];
+        flush_begin();
         half_chunk(reA, imA, a_w, o, 0);
         half_chunk(reB, imB, a_w + 32u, o + 8, 4);
         if (LAYOUT == 0) {
@@ -416,6 +436,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         }
       }
     }
+    flush_begin();
 #pragma unroll
     for (int j = 0; j < 8; ++j) flush_col(j);
   } else if (warp == TC_EW) {
