@@ -390,6 +390,13 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         mbar_wait(BAR(2 + nbuf), (uint32_t)((((it + 1) >> 1) & 1) ^ 1));
         build_a(next, nbuf);
       }
+      if (next + gridDim.x < n_tiles) {                   // the window of the tile after next: into L1 a whole tile early
+        unsigned long long colp = cb + (next + gridDim.x) * TC_M + m;
+        if (colp >= ce) colp = ce - 1;
+        const sig_t* xp = x + (colp * g.hop - off);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(xp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + 2 * TC_HALF - 1));
+      }
       const unsigned long long tile_col0 = cb + tile * TC_M;
       const unsigned long long warp_col0 = tile_col0 + (unsigned long long)(qd * 32 + sw * 8);   // first of the warp's 8 store columns
       const int wcols = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 8ull ? (ce - warp_col0) : 8ull);
