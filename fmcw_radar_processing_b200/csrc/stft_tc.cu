@@ -112,6 +112,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
                  "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&a)[16], float (&b)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]),
+                 "=f"(a[8]), "=f"(a[9]), "=f"(a[10]), "=f"(a[11]), "=f"(a[12]), "=f"(a[13]), "=f"(a[14]), "=f"(a[15]),
+                 "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]), "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]),
+                 "=f"(b[8]), "=f"(b[9]), "=f"(b[10]), "=f"(b[11]), "=f"(b[12]), "=f"(b[13]), "=f"(b[14]), "=f"(b[15])
+               : "r"(taddr) : "memory");
+}
 // wait for this thread's outstanding tcgen05.ld and tie the destination registers to the wait, so that no use of
 // them can be scheduled above it
 __device__ __forceinline__ void tmem_wait_ld(float (&a)[16], float (&b)[16]) {
@@ -407,10 +416,8 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         const uint32_t c0 = t_lane + (uint32_t)(ts * 2 * TC_N);
         mbar_wait(BAR(8 + ts), (uint32_t)((cseq >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tmem_ld16(c0, reA);
-        tmem_ld16(c0 + TC_N, imA);
-        tmem_ld16(c0 + 16, reB);
-        tmem_ld16(c0 + TC_N + 16, imB);
+        tmem_ld32(c0, reA, reB);
+        tmem_ld32(c0 + TC_N, imA, imB);
         tmem_wait_ld(reA, imA);
         tmem_wait_ld(reB, imB);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
