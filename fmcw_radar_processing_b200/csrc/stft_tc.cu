@@ -62,11 +62,6 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 // canonical K-major, non-swizzled operand layout: (row/8)*SBO + (k/4)*128 + (row%8)*16 + (k%4)*4 bytes
 __host__ __device__ __forceinline__ int tc_off_floats(int row, int k) {
   return (row >> 3) * (TC_K * 8) + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
@@ -106,12 +101,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
-                 "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
-               : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&a)[16], float (&b)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -130,12 +119,6 @@ __device__ __forceinline__ void tmem_wait_ld(float (&a)[16], float (&b)[16]) {
   asm volatile("" : "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]),
                     "+f"(b[8]), "+f"(b[9]), "+f"(b[10]), "+f"(b[11]), "+f"(b[12]), "+f"(b[13]), "+f"(b[14]), "+f"(b[15]));
 }
-__device__ __forceinline__ float lds32(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts64(uint32_t a, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory"); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   float2 r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
@@ -149,7 +132,6 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
         "l"(*reinterpret_cast<unsigned long long*>(&c)));
   return r;
 }
-__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 // volatile: keeps its place among the (volatile) shared-memory and global accesses of the epilogue loop, so the
 // MUFU work stays spread over the loop instead of being bunched by the scheduler
