@@ -152,6 +152,7 @@ def workload_config(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--no-mailbox", action="store_true", help="N>1: NCCL collectives instead of the peer-memory mailboxes")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=5000)
@@ -203,6 +204,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     sharded = ShardedRun(h, frame_counts=[n] * world) if world > 1 else None
+    peer_mailbox = bool(sharded.use_peer_mailbox()) if (sharded is not None and not args.no_mailbox) else False
 
     def step_device():
         if sharded is None:
@@ -365,6 +367,9 @@ def main():
             "data": "synthetic", "config": workload_config(args, cfg), "roofline": roofline, "cpu_baseline": cb,
             "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps, "clocks": sampler.summary(),
             "info": {k: info[k] for k in ("n_detected", "L_total", "nfft", "ncol_total", "ncol_local", "n_dtft_bins", "n_refined")}}
+    if world > 1:
+        line["config"]["shard_exchange"] = ("peer-memory mailboxes over NVLink (headers + max inside the kernels); NCCL for the "
+                                            "track gather" if peer_mailbox else "NCCL all-gather + all-reduce + track gather")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

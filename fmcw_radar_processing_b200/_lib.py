@@ -71,6 +71,11 @@ EXPORTS = {
     "fmcw_shard_pack": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fmcw_shard_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "fmcw_shard_stft": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(fmcw_stft_out)]),
+    "fmcw_mailbox_bytes": (C.c_uint64, []),
+    "fmcw_mailbox_post_heads": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint64]),
+    "fmcw_mailbox_plan": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint64]),
+    "fmcw_mailbox_stft": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint64,
+                                    C.POINTER(fmcw_stft_out)]),
     "fmcw_stft_axes": (C.c_int, [C.POINTER(fmcw_config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmcw_range_spectrum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),

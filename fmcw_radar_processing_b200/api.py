@@ -256,6 +256,28 @@ class FmcwCuda:
         self._order_after(dev)
         return intensity
 
+    # ---- sharded path over peer-memory mailboxes (NVLink stores + flags, no collective between the steps) ----
+    def mailbox_bytes(self) -> int:
+        return int(self.lib.fmcw_mailbox_bytes())
+
+    @staticmethod
+    def _mailbox_array(ptrs):
+        return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+    def mailbox_post_heads(self, ptrs, rank: int, step: int):
+        """``ptrs[r]``: device address of rank r's mailbox as mapped in this process."""
+        self._check(self.lib.fmcw_mailbox_post_heads(self._h, self._mailbox_array(ptrs), len(ptrs), rank, step))
+
+    def mailbox_plan(self, ptrs, rank: int, step: int):
+        self._check(self.lib.fmcw_mailbox_plan(self._h, self._mailbox_array(ptrs), len(ptrs), rank, step))
+
+    def mailbox_stft(self, ptrs, rank: int, step: int, intensity, layout: int = _lib.LAYOUT_TIME_MAJOR):
+        so = self._stft_struct(intensity, layout)
+        dev = self._order_before(intensity)
+        self._check(self.lib.fmcw_mailbox_stft(self._h, self._mailbox_array(ptrs), len(ptrs), rank, step, C.byref(so)))
+        self._order_after(dev)
+        return intensity
+
     # ---- extras ----
     def range_spectrum(self, iq, frame: int, chirp: int) -> np.ndarray:
         """abs(range_fft(:, chirp)) of one frame (RP:410-411), 0-based indices."""

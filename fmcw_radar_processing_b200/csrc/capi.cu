@@ -127,7 +127,8 @@ struct fmcw_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;            // look-ahead STFT plan, concurrent with the frame chain
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool lookahead = false;
+  bool lookahead = false;     // a look-ahead plan is in flight on the side stream (ev_join)
+  uint32_t mb_world = 0, mb_rank = 0;   // mailbox path: layout of the last pass (assumed again by the look-ahead plan)
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   std::string err;
   // chain tables
@@ -136,7 +137,7 @@ struct fmcw_handle {
   // STFT tables
   StftTables st{};
   StftGeom geom{};
-  DevBuf plan, bins, kcb, wdc, qpos, aq, qend, coef, swin, hard, derr;
+  DevBuf plan, bins, kcb, wdc, qpos, aq, qend, coef, swin, hard, derr, gmax;
   // scratch
   DevBuf tcb, colub;
   DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, o_slow64, f32_stage, xc, det_list, ndet, inten, synth_tab;
@@ -230,8 +231,9 @@ fmcw_status read_info(fmcw_handle* h) {
     const char* why = derr == -2 ? "more DTFT bins than the plan tables hold" :
                       derr == -3 ? "a query chunk exceeds the shared-memory bin budget" :
                       derr == -4 ? "intensity capacity_cols is smaller than the column count" :
-                      derr == -5 ? "too many columns need the exhaustive max search" : "device-side failure";
-    return fail(h, derr == -4 ? FMCW_ERR_SIZE : FMCW_ERR_CUDA, why);
+                      derr == -5 ? "too many columns need the exhaustive max search" :
+                      derr == -6 ? "a rank never posted to the mailbox (timeout)" : "device-side failure";
+    return fail(h, derr == -4 ? FMCW_ERR_SIZE : derr == -6 ? FMCW_ERR_STATE : FMCW_ERR_CUDA, why);
   }
   return FMCW_OK;
 }
@@ -323,6 +325,25 @@ fmcw_status copy_frame_outputs(fmcw_handle* h, uint64_t n, const fmcw_frame_out*
   return FMCW_OK;
 }
 
+// Every plan launch first joins a look-ahead plan that may be in flight; the plan kernel then confirms the
+// assumed layout (spec_mode 2) or plans again.
+static cudaError_t join_lookahead(fmcw_handle* h, int& spec_mode) {
+  spec_mode = 0;
+  if (!h->lookahead) return cudaSuccess;
+  h->lookahead = false;
+  spec_mode = 2;
+  return cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+}
+static fmcw_status fork_lookahead(fmcw_handle* h, uint64_t L_total, uint64_t offset, uint64_t L_local, uint64_t L_avail) {
+  CK(cudaEventRecord(h->ev_fork, h->stream), "event");
+  CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "fork look-ahead plan");
+  CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks,
+                      h->side, nullptr, 0, 0, nullptr, 1), "look-ahead stft plan");
+  CK(cudaEventRecord(h->ev_join, h->side), "event");
+  h->lookahead = true;
+  return FMCW_OK;
+}
+
 // plan (+ max) + main on the signal held in h->xc.  d_ndet != null: sizes come from the device.
 fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, uint64_t offset, uint64_t L_local,
                      uint64_t L_avail, bool compute_max, double pmax_override, const fmcw_stft_out* sout,
@@ -343,12 +364,11 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
     cap = need; d_ld = need;
   }
   if (!h->planned) {
-    const int spec_mode = (from_device_count && h->lookahead) ? 2 : 0;
-    if (spec_mode) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0), "join look-ahead plan");
+    int spec_mode = 0;
+    CK(join_lookahead(h, spec_mode), "join look-ahead plan");
     CK(launch_stft_plan(h->st, h->geom, from_device_count ? h->ndet.as<unsigned long long>() : nullptr,
                         h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks, h->stream,
                         nullptr, 0, 0, nullptr, spec_mode), "stft plan kernel");
-    h->lookahead = false;
     h->planned = true; h->plan_L = L_total; h->plan_off = offset; h->plan_avail = L_avail;
     if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream), "stft max kernels");
   }
@@ -535,7 +555,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   h->st.hard_cap = 1u << 20;
   ok(h->hard.ensure((size_t)h->st.hard_cap * 4));
   ok(h->tcb.ensure(stft_tc_table_bytes(nb_max) + 256));
-  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16));
+  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16)); ok(h->gmax.ensure(16));
   if (e == cudaSuccess) {
     ok(cudaMemsetAsync(h->plan.p, 0, sizeof(StftPlan), h->stream));
     ok(cudaMemsetAsync(h->derr.p, 0, 16, h->stream));
@@ -553,8 +573,9 @@ void fmcw_destroy(fmcw_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->side) cudaStreamSynchronize(h->side);
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
-                   &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->iq_stage, &h->o_rmax, &h->o_det,
+                   &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
                    &h->synth_tab, &h->tcb, &h->colub};
   for (DevBuf* b : all) b->release();
@@ -618,6 +639,15 @@ fmcw_status fmcw_process_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_fr
   cudaSetDevice(h->device);
   FrameDev d{};
   bool any_host = false;
+  if (h->mb_world > 0 && !h->lookahead) {
+    // mailbox path: plan ahead for "every rank detects a target in each of its (equally many) frames"
+    const uint64_t L_loc = n_frames * h->cfg.num_chirps_per_frame, hw = h->cfg.window_length - 1;
+    const uint64_t after = (uint64_t)(h->mb_world - 1 - h->mb_rank) * L_loc;
+    if (L_loc * h->mb_world >= h->cfg.window_length) {
+      fmcw_status fs = fork_lookahead(h, L_loc * h->mb_world, L_loc * h->mb_rank, L_loc, L_loc + (after < hw ? after : hw));
+      if (fs != FMCW_OK) return fs;
+    }
+  }
   fmcw_status s = run_frames(h, iq, n_frames, out, d, any_host);
   if (s != FMCW_OK) return s;
   s = copy_frame_outputs(h, n_frames, out, d);
@@ -648,12 +678,8 @@ fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const
   if (L_spec >= h->cfg.window_length) {
     // look-ahead: plan the STFT for "every frame detects a target" on a side stream while the frame chain runs;
     // the real plan launch confirms it on the device (or plans again if the detection count differs)
-    CK(cudaEventRecord(h->ev_fork, h->stream), "event");
-    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "fork look-ahead plan");
-    CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, L_spec, 0, L_spec, L_spec, h->n_chunks, h->side,
-                        nullptr, 0, 0, nullptr, 1), "look-ahead stft plan");
-    CK(cudaEventRecord(h->ev_join, h->side), "event");
-    h->lookahead = true;
+    fmcw_status fs = fork_lookahead(h, L_spec, 0, L_spec, L_spec);
+    if (fs != FMCW_OK) return fs;
   }
   fmcw_status s = run_frames(h, iq, n_frames, fout, d, any_host);
   if (s != FMCW_OK) return s;
@@ -753,8 +779,10 @@ fmcw_status fmcw_stft_local_max(fmcw_handle* h, uint64_t L_total, uint64_t sampl
   if (L_total < h->cfg.window_length) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length slow-time samples");
   const uint64_t L = h->n_det_host * h->cfg.num_chirps_per_frame;
   if (sample_offset + L > L_total) return fail(h, FMCW_ERR_SIZE, "shard exceeds L_total");
+  int spec_mode = 0;
+  CK(join_lookahead(h, spec_mode), "join look-ahead plan");
   CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, L_total, sample_offset, L, L + h->halo,
-                      h->n_chunks, h->stream), "stft plan kernel");
+                      h->n_chunks, h->stream, nullptr, 0, 0, nullptr, spec_mode), "stft plan kernel");
   h->planned = true; h->plan_L = L_total; h->plan_off = sample_offset; h->plan_avail = L + h->halo;
   CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream), "stft max kernels");
   fmcw_status s = read_info(h);
@@ -799,8 +827,10 @@ fmcw_status fmcw_shard_plan(fmcw_handle* h, const double* gathered_dev, uint32_t
   if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
   if (rank >= world) return fail(h, FMCW_ERR_SIZE, "rank >= world");
   if (!is_device_ptr(gathered_dev) || !is_device_ptr(local_max_dev)) return fail(h, FMCW_ERR_POINTER, "device memory required");
+  int spec_mode = 0;
+  CK(join_lookahead(h, spec_mode), "join look-ahead plan");
   CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
-                      gathered_dev, world, rank, h->xc.as<sig_t>()), "stft plan kernel");
+                      gathered_dev, world, rank, h->xc.as<sig_t>(), spec_mode), "stft plan kernel");
   CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream, local_max_dev), "stft max kernels");
   h->planned = true; h->have_info = false;
   return FMCW_OK;
@@ -818,6 +848,79 @@ fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const 
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
   CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
                       h->derr.as<int>(), h->stream, global_max_dev), "stft main kernel");
+  CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
+  h->have_info = false;
+  return FMCW_OK;
+}
+
+uint64_t fmcw_mailbox_bytes(void) { return (uint64_t)MAILBOX_BYTES; }
+
+static fmcw_status mailbox_args(fmcw_handle* h, void* const* mailboxes, uint32_t world, uint32_t rank, uint64_t step,
+                                MailboxSet& mb) {
+  if (world == 0 || world > MAILBOX_MAX_WORLD) return fail(h, FMCW_ERR_SIZE, "world must be 1..64");
+  if (rank >= world) return fail(h, FMCW_ERR_SIZE, "rank >= world");
+  if (step == 0) return fail(h, FMCW_ERR_SIZE, "step numbers start at 1");
+  if (h->cfg.window_length > MAILBOX_MAX_WIN) return fail(h, FMCW_ERR_CONFIG, "window_length too large for the mailbox");
+  for (uint32_t r = 0; r < MAILBOX_MAX_WORLD; ++r) mb.ptr[r] = r < world ? mailboxes[r] : nullptr;
+  for (uint32_t r = 0; r < world; ++r)
+    if (!mb.ptr[r]) return fail(h, FMCW_ERR_POINTER, "null mailbox pointer");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_mailbox_post_heads(fmcw_handle* h, void* const* mailboxes, uint32_t world, uint32_t rank, uint64_t step) {
+  if (!h || !mailboxes) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  MailboxSet mb;
+  fmcw_status s = mailbox_args(h, mailboxes, world, rank, step, mb);
+  if (s != FMCW_OK) return s;
+  CK(launch_mailbox_post_heads(h->xc.as<sig_t>(), h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame,
+                               h->cfg.window_length, mb, world, rank, step, h->stream), "mailbox post heads kernel");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_mailbox_plan(fmcw_handle* h, void* const* mailboxes, uint32_t world, uint32_t rank, uint64_t step) {
+  if (!h || !mailboxes) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done) return fail(h, FMCW_ERR_STATE, "no frames processed");
+  MailboxSet mb;
+  fmcw_status s = mailbox_args(h, mailboxes, world, rank, step, mb);
+  if (s != FMCW_OK) return s;
+  void* own = mb.ptr[rank];
+  int spec_mode = 0;
+  CK(join_lookahead(h, spec_mode), "join look-ahead plan");
+  CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
+                      mailbox_heads(own), world, rank, h->xc.as<sig_t>(), spec_mode, mailbox_flag_heads(own), step),
+     "stft plan kernel");
+  h->mb_world = world; h->mb_rank = rank;
+  CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream, h->gmax.as<double>()), "stft max kernels");
+  CK(launch_mailbox_post_max(h->gmax.as<double>(), mb, world, rank, step, h->stream), "mailbox post max kernel");
+  h->planned = true; h->have_info = false;
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_mailbox_stft(fmcw_handle* h, void* const* mailboxes, uint32_t world, uint32_t rank, uint64_t step,
+                              const fmcw_stft_out* sout) {
+  if (!h || !mailboxes || !sout || !sout->intensity) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->frames_done || !h->planned) return fail(h, FMCW_ERR_STATE, "fmcw_mailbox_plan must run first");
+  if (!is_device_ptr(sout->intensity)) return fail(h, FMCW_ERR_POINTER, "device memory required");
+  if (sout->layout > 1) return fail(h, FMCW_ERR_CONFIG, "unknown intensity layout");
+  MailboxSet mb;
+  fmcw_status s = mailbox_args(h, mailboxes, world, rank, step, mb);
+  if (s != FMCW_OK) return s;
+  const uint64_t ld = sout->ld_cols ? sout->ld_cols : sout->capacity_cols;
+  CK(launch_mailbox_collect_max(mb.ptr[rank], world, step, h->gmax.as<double>() + 1, h->derr.as<int>(), h->stream),
+     "mailbox collect max kernel");
+  CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
+  CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
+                      h->derr.as<int>(), h->stream, h->gmax.as<double>() + 1), "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
   return FMCW_OK;

@@ -56,7 +56,7 @@ cudaError_t launch_compact(const CompactParams& p, cudaStream_t st);
 
 // ---- STFT plan (device resident; RP:273, 293-299 restated) ----------------------------------------
 struct StftPlan {
-  unsigned long long L_total, nfft, ncol_total, col_begin, col_end, sample_offset, L_avail;
+  unsigned long long L_total, nfft, ncol_total, col_begin, col_end, sample_offset, L_avail, L_local;
   int log2nfft, nb, nq, n_chunks, valid;
   unsigned int n_hard, n_refined, task_counter, ticket_r, ticket_h;
   int spec_state;               // 1: planned ahead for the length in L_total (not yet confirmed), 2: confirmed, 0: none
@@ -98,7 +98,8 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
                              cudaStream_t st, const double* gathered = nullptr, uint32_t world = 0, uint32_t rank = 0,
-                             sig_t* xc = nullptr, int spec_mode = 0);
+                             sig_t* xc = nullptr, int spec_mode = 0, const unsigned long long* wait_flags = nullptr,
+                             unsigned long long wait_step = 0);
 cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const sig_t* x, cudaStream_t st,
                             double* export_dst = nullptr);
 cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
@@ -116,6 +117,46 @@ cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const si
 int stft_variant();            // FMCW_STFT_VARIANT: -1 (default) tensor cores, 0..4 CUDA-core variants
 
 cudaError_t launch_f32_to_sig(const float* src, sig_t* dst, unsigned long long n, cudaStream_t st);
+
+// ---- peer-memory mailboxes of the sharded path (mailbox.cu) ------------------------------------------------
+constexpr uint32_t MAILBOX_MAX_WORLD = 64;
+constexpr uint32_t MAILBOX_MAX_WIN = 400;
+constexpr unsigned long long MAILBOX_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr size_t MAILBOX_BYTES = (size_t)MAILBOX_MAX_WORLD * (8 + 8 + 8) + (size_t)MAILBOX_MAX_WORLD * MAILBOX_MAX_WIN * 8;
+struct MailboxSet { void* ptr[MAILBOX_MAX_WORLD]; };   // the mailbox of every rank as mapped on this rank
+__host__ __device__ inline unsigned long long* mailbox_flag_heads(void* m) { return reinterpret_cast<unsigned long long*>(m); }
+__host__ __device__ inline unsigned long long* mailbox_flag_max(void* m) { return reinterpret_cast<unsigned long long*>(m) + MAILBOX_MAX_WORLD; }
+__host__ __device__ inline double* mailbox_max(void* m) { return reinterpret_cast<double*>(m) + 2 * MAILBOX_MAX_WORLD; }
+__host__ __device__ inline double* mailbox_heads(void* m) { return reinterpret_cast<double*>(m) + 3 * MAILBOX_MAX_WORLD; }
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long mailbox_ld_flag(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long mailbox_global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// true when flags[i] >= step before the timeout (threads i >= n return true at once)
+__device__ __forceinline__ bool mailbox_wait(const unsigned long long* flags, uint32_t i, uint32_t n, unsigned long long step) {
+  if (i >= n) return true;
+  const unsigned long long t0 = mailbox_global_ns();
+  while (mailbox_ld_flag(flags + i) < step) {
+    __nanosleep(64);
+    if (mailbox_global_ns() - t0 > MAILBOX_TIMEOUT_NS) return false;
+  }
+  return true;
+}
+#endif
+cudaError_t launch_mailbox_post_heads(const sig_t* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win,
+                                      const MailboxSet& mb, uint32_t world, uint32_t rank, unsigned long long step,
+                                      cudaStream_t st);
+cudaError_t launch_mailbox_post_max(const double* local_max, const MailboxSet& mb, uint32_t world, uint32_t rank,
+                                    unsigned long long step, cudaStream_t st);
+cudaError_t launch_mailbox_collect_max(void* own, uint32_t world, unsigned long long step, double* gmax, int* d_err,
+                                       cudaStream_t st);
 
 // ---- synthetic scene generator ------------------------------------------------------------------
 cudaError_t launch_synth(const double* tables, uint32_t n_scat, uint64_t seed, uint64_t frame0, uint64_t n_frames,

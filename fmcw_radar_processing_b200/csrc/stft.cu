@@ -23,28 +23,32 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          unsigned long long sample_offset,
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
                                                          int n_chunks_req, int coef_rows, const double* __restrict__ gathered,
-                                                         uint32_t world, uint32_t rank, sig_t* __restrict__ xc, int spec_mode) {
+                                                         uint32_t world, uint32_t rank, sig_t* __restrict__ xc, int spec_mode,
+                                                         const unsigned long long* wait_flags, unsigned long long wait_step) {
   __shared__ int s_scan[1024];
   __shared__ int s_wsum[32];
   __shared__ unsigned long long s_nfft;
   __shared__ int s_valid;
   __shared__ int s_hit;
+  __shared__ unsigned long long s_lay[4];   // L_total, L_local, L_avail, sample_offset of this pass
   StftPlan* P = t.plan;
-  // spec_mode 1: planning ahead (side stream, concurrently with the frame chain) for an assumed length;
-  // spec_mode 2: the real length is known: if it equals the assumed one the tables stand, otherwise plan again
-  if (threadIdx.x == 0) {
-    int hit = 0;
-    if (spec_mode == 2 && d_ndet && P->spec_state == 1 && P->valid > 0 && P->L_total == *d_ndet * PN) hit = 1;
-    s_hit = hit;
-    if (hit) P->spec_state = 2;
+  if (wait_flags) {
+    // mailbox path: the shard headers arrive by peer stores; wait for the flag of every rank (mailbox.cu)
+    __shared__ int s_late;
+    if (threadIdx.x == 0) s_late = 0;
+    __syncthreads();
+    if (!mailbox_wait(wait_flags, threadIdx.x, world, wait_step)) s_late = 1;
+    __syncthreads();
+    if (s_late) { if (threadIdx.x == 0) { P->valid = -6; P->nb = 0; P->n_chunks = 0; } return; }
   }
-  __syncthreads();
-  if (s_hit) return;
+  // spec_mode 1: planning ahead (side stream, concurrently with the frame chain) for an assumed layout;
+  // spec_mode 2: the real layout is known: if it equals the assumed one the tables stand, otherwise plan again
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nq = (int)g.nq;
   const int win = (int)g.win, hop = (int)g.hop, nov = win - hop;
 
   if (tid == 0) {
+    s_hit = 0;
     unsigned long long L = L_total_host, Lloc = L_local_host, Lav = L_avail_host;
     if (gathered) {
       // sharded run: global length, this shard's offset and the halo (the win-1 samples that follow this shard,
@@ -66,7 +70,19 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
       }
       L = total; Lloc = mine; Lav = mine + got; sample_offset = soff;
     } else if (d_ndet && spec_mode != 1) { L = *d_ndet * PN; Lloc = L; Lav = L; }
-    P->L_total = L; P->sample_offset = sample_offset; P->L_avail = Lav;
+    if (spec_mode == 2 && P->spec_state == 1 && P->valid > 0 && P->L_total == L && P->sample_offset == sample_offset &&
+        P->L_avail == Lav && P->L_local == Lloc) {
+      P->spec_state = 2;
+      s_hit = 1;
+    }
+    s_lay[0] = L; s_lay[1] = Lloc; s_lay[2] = Lav; s_lay[3] = sample_offset;
+  }
+  __syncthreads();
+  if (s_hit) return;
+  if (tid == 0) {
+    const unsigned long long L = s_lay[0], Lloc = s_lay[1], Lav = s_lay[2];
+    sample_offset = s_lay[3];
+    P->L_total = L; P->sample_offset = sample_offset; P->L_avail = Lav; P->L_local = Lloc;
     P->n_hard = 0; P->n_refined = 0; P->lb_max = 0.f; P->pmax_raw = 0.0; P->task_counter = 0; P->ticket_r = 0; P->ticket_h = 0;
     P->spec_state = (spec_mode == 1) ? 1 : 0;
     int ok = (L >= (unsigned long long)win) ? 1 : 0;
@@ -757,10 +773,11 @@ int stft_variant() {
 cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsigned long long* d_ndet, uint32_t PN,
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
-                             cudaStream_t st, const double* gathered, uint32_t world, uint32_t rank, sig_t* xc, int spec_mode) {
+                             cudaStream_t st, const double* gathered, uint32_t world, uint32_t rank, sig_t* xc, int spec_mode,
+                             const unsigned long long* wait_flags, unsigned long long wait_step) {
   const bool tc = (g.win == 20 && stft_variant() < 0);
   stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks,
-                                       tc ? 2 : 0, gathered, world, rank, xc, spec_mode);
+                                       tc ? 2 : 0, gathered, world, rank, xc, spec_mode, wait_flags, wait_step);
   if (!tc) { stft_coef_kernel<<<128, 256, 0, st>>>(t, g, spec_mode); return cudaGetLastError(); }
   return launch_stft_tc_prepare(t, g, t.tcB, t.nb_max, st, spec_mode);
   return cudaGetLastError();

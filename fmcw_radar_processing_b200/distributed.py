@@ -10,6 +10,11 @@ through the concatenated slow-time signal only, so exactly three small collectiv
 2. one all-reduce(max) of the scalar normalisation max(P) (RP:282-283);
 3. one all-gather of the per-frame track (range bin, Doppler bin, strength) for the range/speed payload.
 
+On a CUDA node whose GPUs can map each other's memory (NVLink/NVSwitch), collectives 1 and 2 are replaced by
+peer-memory mailboxes (``PeerMailbox``): the kernels of every rank store the header / the maximum straight into
+all ranks' mailboxes and the consumers wait on flags on the device, so a pass has no collective call and no
+stream hand-off on its critical path; NCCL remains for the track gather (3), which overlaps the STFT.
+
 Column ownership: a spectrogram column belongs to the shard that owns its first sample, so columns are
 neither duplicated nor lost.  Everything in this file except ``ShardedRun`` is backend agnostic and is
 covered by world_size-2 gloo tests on CPU.
@@ -94,6 +99,40 @@ def owned_columns(offset: int, L_local: int, L_total: int, window_length: int, o
     return min(b, e), e, ncol
 
 
+class PeerMailbox:
+    """One mailbox per rank in symmetric (peer-mapped) device memory; ``ptrs[r]`` is rank r's mailbox as
+    addressable from this process.  Built with ``torch.distributed._symmetric_memory`` (CUDA VMM / IPC
+    handles exchanged through the group's store); ``PeerMailbox.create`` returns None when that is not available,
+    and callers fall back to the NCCL collectives."""
+
+    def __init__(self, buf, ptrs, rank):
+        self.buf, self.ptrs, self.rank, self.step = buf, list(ptrs), rank, 0
+
+    @classmethod
+    def create(cls, handle, group=None):
+        if not torch.cuda.is_available() or dist.get_backend(group) != "nccl":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = torch.device("cuda", torch.cuda.current_device())
+            n = (handle.mailbox_bytes() + 7) // 8
+            buf = symm_mem.empty(n, dtype=torch.float64, device=dev)
+            buf.zero_()
+            g = group if group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, g.group_name)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            torch.cuda.synchronize(dev)          # the mailbox is zeroed (use_peer_mailbox adds the barrier)
+            return cls(buf, ptrs, dist.get_rank(group))
+        except Exception as e:                   # no peer access / symmetric memory not supported here
+            import warnings
+            warnings.warn(f"peer-memory mailboxes unavailable, using NCCL collectives: {e}")
+            return None
+
+    def next_step(self) -> int:
+        self.step += 1
+        return self.step
+
+
 class ShardedRun:
     """One rank's share of a frame-sharded recording on its GPU."""
 
@@ -101,6 +140,20 @@ class ShardedRun:
         self.h = handle
         self.group = group
         self.frame_counts = frame_counts      # frames per rank (static); gathered once if not given
+        self.mailbox = None                   # PeerMailbox: set by use_peer_mailbox()
+
+    def use_peer_mailbox(self) -> bool:
+        """Collective call (every rank): switches ``step_async`` to the peer-memory hand-offs when the GPUs of
+        this node can map each other's memory.  Returns whether they are in use."""
+        self.mailbox = PeerMailbox.create(self.h, self.group)
+        # all ranks must take the same path
+        ok = torch.tensor([1 if self.mailbox is not None else 0], device="cuda" if torch.cuda.is_available() else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.mailbox = None
+        else:
+            dist.barrier(group=self.group)    # every mailbox is zeroed before anyone posts
+        return self.mailbox is not None
 
     def _async_buffers(self, dev):
         if getattr(self, "_bufs", None) is None:
@@ -135,6 +188,18 @@ class ShardedRun:
         afterwards with ``handle.info()``."""
         h = self.h
         dev = iq.device
+        mb = self.mailbox
+        if mb is not None:
+            # peer-memory path: three library calls on the handle's stream, the exchanges happen inside the kernels
+            step = mb.next_step()
+            h.process_frames(iq, out)
+            if gather:
+                torch.cuda.current_stream(dev).wait_stream(self._async_buffers(dev)["lib_stream"])   # track columns are written
+            h.mailbox_post_heads(mb.ptrs, mb.rank, step)
+            h.mailbox_plan(mb.ptrs, mb.rank, step)
+            track = self._gather_track_async(out, dev) if gather else None              # collective 3 (overlaps plan/STFT)
+            h.mailbox_stft(mb.ptrs, mb.rank, step, intensity, layout)
+            return dict(track=track)
         b = self._async_buffers(dev)
         lib, cur = b["lib_stream"], torch.cuda.current_stream(dev)
         ws, rank = dist.get_world_size(self.group), dist.get_rank(self.group)

@@ -187,6 +187,25 @@ FMCW_API fmcw_status fmcw_shard_plan(fmcw_handle* h, const double* gathered_dev,
                                      double* local_max_dev);
 FMCW_API fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const fmcw_stft_out* sout);
 
+/* Peer-memory form of the same path (NVLink/NVSwitch, no collective call between the steps): every rank owns a
+ * zero-initialised "mailbox" of fmcw_mailbox_bytes() bytes of device memory that is mapped on all ranks (CUDA IPC /
+ * VMM, e.g. torch symmetric memory).  mailboxes[r] is rank r's mailbox as addressable from THIS process (a host
+ * array of world device pointers, mailboxes[rank] being the own one).  step is the same strictly increasing number
+ * (>= 1) on all ranks for one pass.
+ *   fmcw_process_frames -> fmcw_mailbox_post_heads: stores {L_local, first window_length-1 samples} into every
+ *     mailbox and raises this rank's flag there;
+ *   fmcw_mailbox_plan: waits (on the device) for all world headers, plans, searches the local maximum and posts it;
+ *   fmcw_mailbox_stft: waits for all world maxima, takes their maximum and runs the STFT of the own columns.
+ * Replaces nothing in the reference (single-process MATLAB); a rank that never posts makes the waiting kernels give
+ * up after 20 s and the pass fail with FMCW_ERR_STATE at the next synchronisation. world <= 64. */
+FMCW_API uint64_t fmcw_mailbox_bytes(void);
+FMCW_API fmcw_status fmcw_mailbox_post_heads(fmcw_handle* h, void* const* mailboxes, uint32_t world, uint32_t rank,
+                                             uint64_t step);
+FMCW_API fmcw_status fmcw_mailbox_plan(fmcw_handle* h, void* const* mailboxes, uint32_t world, uint32_t rank,
+                                       uint64_t step);
+FMCW_API fmcw_status fmcw_mailbox_stft(fmcw_handle* h, void* const* mailboxes, uint32_t world, uint32_t rank,
+                                       uint64_t step, const fmcw_stft_out* sout);
+
 /* Host-side axes in float64: T (RP:276) for columns [col_begin, col_begin+ncol) and
  * log_freq_bins (RP:293-296).  Either pointer may be NULL. */
 FMCW_API fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, uint64_t col_begin, uint64_t ncol,
