@@ -640,7 +640,7 @@ stft_main_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* _
 // and re-enters through the tabulated window response (same DC split as the tensor-core kernel).  Time-major
 // output is staged per warp like in stft_main_kernel.  This is the path of the C5 window / hop sweep.
 template <int LAYOUT>
-__global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x,
+__global__ void __launch_bounds__(128) stft_generic_serial_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x,
                                                            float* __restrict__ out, unsigned long long capacity_cols,
                                                            unsigned long long ld_cols, int* d_err) {
   const StftPlan* P = t.plan;
@@ -733,6 +733,157 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(StftTables t, StftGeo
 
 // ------------------------------------------------------------------------------------------------
 // device-side hand-offs of the sharded path (no host round trip between the collectives)
+// ------------------------------------------------------------------------------------------------
+// Generic window length up to 256 (any hop, odd lengths), the C5 sweep: a CTA task = 128 columns x one query chunk,
+// handed out by an atomic counter so that recordings with few columns still fill the GPU.  The folded taps of the
+// 128 columns sit in shared memory ([tap][column]); bins are walked in passes of 32: warp w owns 8 bins, a lane 4
+// columns (2 LDS.128 of taps + 4 broadcast LDS.128 of coefficients -> 64 FMAs per tap), the 32 x 128 dB values go
+// through shared memory to the column-owning threads, which run the interp1 and stage time-major rows as the
+// other CUDA-core kernels do.  Mean removal in float64 and the DC term as mean * W(w_bin) as everywhere else.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEN_COLS = 128, GEN_PB = 32, GEN_CFS = 36, GEN_DBS = 33, GEN_QF = 16;
+constexpr int GEN_MAX_WIN = 256;
+
+static size_t generic_tiled_smem(uint32_t win) {
+  const size_t half = win / 2;
+  return (2 * half * GEN_COLS + 2 * half * GEN_CFS + GEN_COLS * GEN_DBS + 4 * 32 * (GEN_QF + 1) + 2 * GEN_COLS + 4) * sizeof(float);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128) stft_generic_tiled_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x,
+                                                                 float* __restrict__ out, unsigned long long capacity_cols,
+                                                                 unsigned long long ld_cols, int* d_err) {
+  StftPlan* P = t.plan;
+  if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
+  constexpr int QF = GEN_QF;
+  extern __shared__ __align__(16) float s_dyn[];
+  const int win = (int)g.win, half = win / 2, odd = win & 1;
+  float* s_eo = s_dyn;                                     // [2*half][128] even / odd parts, column-minor
+  float* s_cf = s_eo + (size_t)2 * half * GEN_COLS;        // [2*half][GEN_CFS] cos (rows < half) / sin of the pass's 32 bins
+  float* s_db = s_cf + (size_t)2 * half * GEN_CFS;         // [128][GEN_DBS] dB of the pass, column-major
+  float* s_stage = s_db + GEN_COLS * GEN_DBS;              // [4 warps][32][QF+1]
+  float* s_xb = s_stage + 4 * 32 * (QF + 1);               // [128] mean * inv
+  float* s_yc = s_xb + GEN_COLS;                           // [128] centre tap of odd windows
+  int* s_task = reinterpret_cast<int*>(s_yc + GEN_COLS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
+  const unsigned long long ncl = ce - cb;
+  if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
+  const int nq = P->nq, nb = P->nb, n_chunks = P->n_chunks;
+  const float inv = (float)(1.0 / sqrt(P->pmax_raw));
+  const unsigned long long n_blk = (ncl + GEN_COLS - 1) / GEN_COLS;
+  const long long n_tasks = (long long)(n_blk * (unsigned long long)n_chunks);
+  const uint32_t a_stage = smem_u32(s_stage) + (uint32_t)(warp * 32 * (QF + 1) * 4);
+  const uint32_t a_st_lane = a_stage + (uint32_t)(lane * (QF + 1) * 4);
+  for (;;) {
+    __syncthreads();                                       // previous task is done with every shared array
+    if (tid == 0) s_task[0] = (int)atomicAdd(&P->task_counter, 1u);
+    __syncthreads();
+    const long long task = s_task[0];
+    if (task >= n_tasks) break;
+    const int ch = (int)(task % n_chunks);
+    const unsigned long long blk = (unsigned long long)(task / n_chunks);
+    const int q0 = P->chunk_q0[ch], q1 = P->chunk_q0[ch + 1];
+    const int p0 = P->chunk_p0[ch];
+    const int np = t.qpos[q1 - 1] + 1 - p0 + 1;            // bin positions [p0, p0 + np)
+    // ---- folded, windowed, mean-free taps of this thread's column ----
+    unsigned long long col = cb + blk * GEN_COLS + tid;
+    const bool act = col < ce;
+    if (!act) col = ce - 1;
+    {
+      const sig_t* xs = x + (col * g.hop - off);
+      double mean_d = 0.0;
+      for (int n = 0; n < win; ++n) mean_d += xs[n];
+      mean_d /= (double)win;
+      const float mean = (float)mean_d;
+      for (int m = 0; m < half; ++m) {
+        const int lo = half - 1 - m, hi = odd ? (half + 1 + m) : (half + m);
+        const float ylo = t.win[lo] * inv * (float)(xs[lo] - (double)mean), yhi = t.win[hi] * inv * (float)(xs[hi] - (double)mean);
+        s_eo[m * GEN_COLS + tid] = ylo + yhi;
+        s_eo[(half + m) * GEN_COLS + tid] = ylo - yhi;
+      }
+      s_yc[tid] = odd ? t.win[half] * inv * (float)(xs[half] - (double)mean) : 0.f;
+      s_xb[tid] = mean * inv;
+    }
+    const unsigned long long warp_col0 = cb + blk * GEN_COLS + (unsigned long long)warp * 32;
+    const int ncols_valid = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 32ull ? (ce - warp_col0) : 32ull);
+    float* out_warp = out + (warp_col0 - cb) * (unsigned long long)nq;
+    float prev = 0.f;
+    int qcur = q0;
+    for (int pb = 0; pb < np; pb += GEN_PB) {
+      __syncthreads();                                     // taps complete; previous pass is done with s_cf and s_db
+      for (int i = tid; i < 2 * half * GEN_PB; i += 128) {
+        const int pp = i / (2 * half), m = i - pp * 2 * half, p = p0 + pb + pp;
+        s_cf[m * GEN_CFS + pp] = (pb + pp < np) ? t.coef[(size_t)p * 2 * half + m] : 0.f;
+      }
+      __syncthreads();
+      {
+        float re[4][8], im[4][8];
+        const float4 yc4 = *reinterpret_cast<const float4*>(s_yc + 4 * lane);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          re[0][j] = yc4.x; re[1][j] = yc4.y; re[2][j] = yc4.z; re[3][j] = yc4.w;
+          im[0][j] = 0.f; im[1][j] = 0.f; im[2][j] = 0.f; im[3][j] = 0.f;
+        }
+        const float* pe = s_eo + 4 * lane;
+        const float* pc = s_cf + 8 * warp;
+#pragma unroll 2
+        for (int m = 0; m < half; ++m) {
+          const float4 e4 = *reinterpret_cast<const float4*>(pe + m * GEN_COLS);
+          const float4 o4 = *reinterpret_cast<const float4*>(pe + (half + m) * GEN_COLS);
+          const float4 c0 = *reinterpret_cast<const float4*>(pc + m * GEN_CFS), c1 = *reinterpret_cast<const float4*>(pc + m * GEN_CFS + 4);
+          const float4 s0 = *reinterpret_cast<const float4*>(pc + (half + m) * GEN_CFS), s1 = *reinterpret_cast<const float4*>(pc + (half + m) * GEN_CFS + 4);
+          const float ev[4] = {e4.x, e4.y, e4.z, e4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
+          const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { re[i][j] = fmaf(ev[i], cv[j], re[i][j]); im[i][j] = fmaf(ov[i], sv[j], im[i][j]); }
+        }
+        const float4 xb4 = *reinterpret_cast<const float4*>(s_xb + 4 * lane);
+        const float xbv[4] = {xb4.x, xb4.y, xb4.z, xb4.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pr = pb + 8 * warp + j;
+          const int p = p0 + (pr < np ? pr : np - 1);
+          const float wd = __ldg(t.wdc + p), kc = __ldg(t.kcb + p);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float r = fmaf(xbv[i], wd, re[i][j]);          // + mean * window DC response
+            s_db[(4 * lane + i) * GEN_DBS + 8 * warp + j] = fmaf(K_DB, lg2_approx(fmaf(r, r, im[i][j] * im[i][j])), kc);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- interp1 of this thread's column over the pass's bins ----
+      const int nbp = (np - pb) < GEN_PB ? (np - pb) : GEN_PB;
+      for (int b = 0; b < nbp; ++b) {
+        const int p = p0 + pb + b;
+        const float db = s_db[tid * GEN_DBS + b];
+        if (pb + b > 0) {
+          int qe = __ldg(t.qend + p);
+          qe = qe > q1 ? q1 : qe;
+          for (; qcur < qe; ++qcur) {
+            const float v = fmaf(__ldg(t.aq + qcur), db - prev, prev);
+            if (LAYOUT == 0) {
+              const int slot = qcur & (QF - 1);
+              sts32(a_st_lane + (uint32_t)(slot * 4), v);
+              if (slot == QF - 1) flush_stage<QF, 32>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - (QF - 1), QF, lane);
+            } else if (act) {
+              out[(unsigned long long)qcur * ld_cols + (col - cb)] = v;
+            }
+          }
+        }
+        prev = db;
+      }
+    }
+    if (LAYOUT == 0) {
+      const int rem = qcur & (QF - 1);
+      if (rem) flush_stage<QF, 32>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - rem, rem, lane);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // msg = {L_local, first win-1 samples} in float64: the shard header that is all-gathered
 __global__ void shard_pack_kernel(const sig_t* __restrict__ xc, const unsigned long long* __restrict__ d_ndet, uint32_t PN,
@@ -834,17 +985,31 @@ cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t
       case 4: return launch_main_variant<10, 1, 16, 256, 4>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
       case 0: return launch_main_variant<10, 2, 16, 256, 3>(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
     }
+  } else if (g.win <= (uint32_t)GEN_MAX_WIN) {
+    const size_t smem = generic_tiled_smem(g.win);
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    cudaError_t e;
+    if (layout == 0) {
+      e = cudaFuncSetAttribute(stft_generic_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      stft_generic_tiled_kernel<0><<<sms * per_sm, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+    } else {
+      e = cudaFuncSetAttribute(stft_generic_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      stft_generic_tiled_kernel<1><<<sms * per_sm, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+    }
   } else {
     const size_t smem = ((size_t)(2 * (g.win / 2)) * 128 + (size_t)(g.win / 2) * 16 + 4 * 32 * 17) * sizeof(float);
     cudaError_t e;
     if (layout == 0) {
-      e = cudaFuncSetAttribute(stft_generic_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(stft_generic_serial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      stft_generic_kernel<0><<<sms * 4, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+      stft_generic_serial_kernel<0><<<sms * 4, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
     } else {
-      e = cudaFuncSetAttribute(stft_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(stft_generic_serial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      stft_generic_kernel<1><<<sms * 4, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
+      stft_generic_serial_kernel<1><<<sms * 4, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
     }
   }
   return cudaGetLastError();
