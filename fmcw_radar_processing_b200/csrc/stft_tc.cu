@@ -17,12 +17,12 @@
 //     (mean * window DC response W(w_bin), tabulated in float64 and split hi + lo), so the large DC term is
 //     never rounded together with the small residual;
 //   * the one-sided doubling (RP:276) is folded into the B operands (sqrt(2) on every bin but DC and Nyquist);
-//   * A tiles are written to shared memory by the epilogue threads (K-major, no swizzle, core matrices of
-//     8 rows x 16 bytes); B tiles (planned once on the device) arrive by 1-D bulk copy (cp.async.bulk) on an
+//   * A tiles are written to shared memory by a dedicated builder warp, one tile ahead (K-major, no swizzle, core
+//     matrices of 8 rows x 16 bytes); B tiles (planned once on the device) arrive by 1-D bulk copy (cp.async.bulk) on an
 //     mbarrier; tcgen05.commit signals the epilogue, which reads the accumulators with tcgen05.ld, takes
 //     |S|^2 -> lg2, interpolates, scales to dB and writes the spectrogram.
-// One CTA per SM (576 threads): warps 0-15 epilogue (lane quarter = warp & 3; the four warps of a quarter each
-// take 16 queries of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer.  TMEM (512 columns), the A
+// One CTA per SM (608 threads): warps 0-15 epilogue (lane quarter = warp & 3; the four warps of a quarter each
+// take 16 queries of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer, warp 18 A-tile builder.  TMEM (512 columns), the A
 // tiles, the B tiles and the output staging rows are double buffered: the MMAs of chunk c+1 and the stores of
 // chunk c-1 overlap the lg2 phase of chunk c.
 #include <cstdlib>
@@ -38,7 +38,7 @@ constexpr int TC_HALF = 10;                            // folded taps
 constexpr int TC_M = 128, TC_N = 128, TC_K = 32;       // UMMA tile; K = 3 x 10 taps + 2 DC slots
 constexpr int TC_QC = TC_N / 2;                        // queries per chunk
 constexpr int TC_EW = 16;                              // epilogue warps
-constexpr int TC_THREADS = (TC_EW + 2) * 32;
+constexpr int TC_THREADS = (TC_EW + 3) * 32;          // + MMA issuer, bulk-copy producer, A-tile builder
 constexpr int TC_A_MAT_BYTES = TC_M * TC_K * 4;        // 16 KB per A operand matrix (E or O)
 constexpr int TC_A_BYTES = 2 * TC_A_MAT_BYTES;
 constexpr int TC_B_MAT_BYTES = TC_N * TC_K * 4;        // 16 KB per B operand matrix (C or S)
@@ -256,7 +256,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
   auto BAR = [&](int i) { return bar0 + (uint32_t)(i * 8); };
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(0 + i), TC_EW); mbar_init(BAR(2 + i), 1);
+      mbar_init(BAR(0 + i), 1); mbar_init(BAR(2 + i), 1);
       mbar_init(BAR(4 + i), 1); mbar_init(BAR(6 + i), 1);
       mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), TC_EW);
     }
@@ -283,49 +283,6 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
     const uint32_t a_stq = smem_u32(s_stg) + (uint32_t)(qd * TC_SQ * 4);       // this quarter's staging rows
     const uint32_t a_st_w = a_stq + (uint32_t)((lane * TC_SROW + sw * 16) * 4);        // store: own column, own 16 queries
     const uint32_t a_st_r = a_stq + (uint32_t)((sw * 8 * TC_SROW + 2 * lane) * 4);     // load: 8 columns, 2 queries per lane
-
-    // A operands of one column: a TF32-exact mean estimate removed in float64, windowed, folded even/odd, split
-    // hi/lo and laid out along K as [hi | hi | lo | M M].  The four warps of a quarter share the work: warp sw
-    // writes K slots 16*(sw&1).. of E (sw < 2) or O.
-    auto build_a = [&](unsigned long long tile, int buf) {
-      unsigned long long col = cb + tile * TC_M + m;
-      if (col >= ce) col = ce - 1;
-      const sig_t* xs = x + (col * g.hop - off);
-      double xd[2 * TC_HALF];
-      double mean_d = 0.0;
-#pragma unroll
-      for (int n = 0; n < 2 * TC_HALF; ++n) { xd[n] = __ldg(xs + n); mean_d += xd[n]; }
-      mean_d *= (1.0 / (2 * TC_HALF));
-      const float M = tf32_rna((float)(mean_d * inv_d));   // DC slot value; mu = M / inv is what the residual removes
-      const double mu = (double)M * sqrt(pmax);
-      float yv[2 * TC_HALF];
-#pragma unroll
-      for (int n = 0; n < 2 * TC_HALF; ++n) yv[n] = s_ws[n] * (float)(xd[n] - mu);
-      const bool even = sw < 2;
-      float hi[TC_HALF], lo[TC_HALF];
-#pragma unroll
-      for (int k = 0; k < TC_HALF; ++k) {
-        const float v = even ? (yv[TC_HALF - 1 - k] + yv[TC_HALF + k]) : (yv[TC_HALF - 1 - k] - yv[TC_HALF + k]);
-        hi[k] = tf32_rna(v);
-        lo[k] = tf32_rna(v - hi[k]);
-      }
-      const float dc = even ? M : 0.f;
-      float* rowp = sA + buf * (TC_A_BYTES / 4) + (even ? 0 : TC_A_MAT_BYTES / 4) + (m >> 3) * (TC_K * 8) + (m & 7) * 4;
-      if ((sw & 1) == 0) {        // slots 0..15: hi[0..9], hi[0..5]
-        *reinterpret_cast<float4*>(rowp + 0 * 32) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(rowp + 1 * 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<float4*>(rowp + 2 * 32) = make_float4(hi[8], hi[9], hi[0], hi[1]);
-        *reinterpret_cast<float4*>(rowp + 3 * 32) = make_float4(hi[2], hi[3], hi[4], hi[5]);
-      } else {                    // slots 16..31: hi[6..9], lo[0..9], dc, dc
-        *reinterpret_cast<float4*>(rowp + 4 * 32) = make_float4(hi[6], hi[7], hi[8], hi[9]);
-        *reinterpret_cast<float4*>(rowp + 5 * 32) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<float4*>(rowp + 6 * 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-        *reinterpret_cast<float4*>(rowp + 7 * 32) = make_float4(lo[8], lo[9], dc, dc);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(0 + buf));              // one arrival per warp
-    };
 
     // the finished chunk still in the staging rows: its 8 columns x 64 queries leave as 256-byte rows while the
     // next chunk's lg2 phase runs
@@ -373,21 +330,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
     float reA[16], imA[16], reB[16], imB[16];              // accumulator halves: one in use, one in flight
 
     unsigned long long it = 0;                            // local tile counter
-    if (blockIdx.x < n_tiles) build_a(blockIdx.x, 0);
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const unsigned long long next = tile + gridDim.x;
-      if (next < n_tiles) {                               // A of the next tile while this tile's chunks are in flight
-        const int nbuf = (int)((it + 1) & 1);
-        mbar_wait(BAR(2 + nbuf), (uint32_t)((((it + 1) >> 1) & 1) ^ 1));
-        build_a(next, nbuf);
-      }
-      if (next + gridDim.x < n_tiles) {                   // the window of the tile after next: into L1 a whole tile early
-        unsigned long long colp = cb + (next + gridDim.x) * TC_M + m;
-        if (colp >= ce) colp = ce - 1;
-        const sig_t* xp = x + (colp * g.hop - off);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(xp));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + 2 * TC_HALF - 1));
-      }
       const unsigned long long tile_col0 = cb + tile * TC_M;
       const unsigned long long warp_col0 = tile_col0 + (unsigned long long)(qd * 32 + sw * 8);   // first of the warp's 8 store columns
       const int wcols = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 8ull ? (ce - warp_col0) : 8ull);
@@ -467,6 +410,56 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
       }
     }
     __syncwarp();
+  } else if (warp == TC_EW + 2) {
+    // ===================== A-tile builder: one warp, four rows (spectrogram columns) per lane =====================
+    // A operands of one column: a TF32-exact mean estimate removed in float64, windowed, folded even/odd, split
+    // hi/lo and laid out along K as [hi | hi | lo | M M] (E) and [hi | hi | lo | 0 0] (O).  The warp runs one tile
+    // ahead of the MMA issuer, so neither the tensor core nor the epilogue warps ever wait for it.
+    unsigned long long it = 0;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      mbar_wait(BAR(2 + buf), (uint32_t)(((it >> 1) & 1) ^ 1));   // the MMAs of the tile that last used this buffer retired
+#pragma unroll 1
+      for (int r = 0; r < TC_M / 32; ++r) {
+        const int m = r * 32 + lane;                       // row of the tile = spectrogram column = TMEM lane
+        unsigned long long col = cb + tile * TC_M + m;
+        if (col >= ce) col = ce - 1;
+        const sig_t* xs = x + (col * g.hop - off);
+        double xd[2 * TC_HALF];
+        double mean_d = 0.0;
+#pragma unroll
+        for (int n = 0; n < 2 * TC_HALF; ++n) { xd[n] = __ldg(xs + n); mean_d += xd[n]; }
+        mean_d *= (1.0 / (2 * TC_HALF));
+        const float M = tf32_rna((float)(mean_d * inv_d));   // DC slot value; mu = M / inv is what the residual removes
+        const double mu = (double)M * sqrt(pmax);
+        float yv[2 * TC_HALF];
+#pragma unroll
+        for (int n = 0; n < 2 * TC_HALF; ++n) yv[n] = s_ws[n] * (float)(xd[n] - mu);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {             // 0: even (E), 1: odd (O)
+          float hi[TC_HALF], lo[TC_HALF];
+#pragma unroll
+          for (int k = 0; k < TC_HALF; ++k) {
+            const float v = part == 0 ? (yv[TC_HALF - 1 - k] + yv[TC_HALF + k]) : (yv[TC_HALF - 1 - k] - yv[TC_HALF + k]);
+            hi[k] = tf32_rna(v);
+            lo[k] = tf32_rna(v - hi[k]);
+          }
+          const float dc = part == 0 ? M : 0.f;
+          float* rowp = sA + buf * (TC_A_BYTES / 4) + part * (TC_A_MAT_BYTES / 4) + (m >> 3) * (TC_K * 8) + (m & 7) * 4;
+          *reinterpret_cast<float4*>(rowp + 0 * 32) = make_float4(hi[0], hi[1], hi[2], hi[3]);     // slots 0..9: hi
+          *reinterpret_cast<float4*>(rowp + 1 * 32) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<float4*>(rowp + 2 * 32) = make_float4(hi[8], hi[9], hi[0], hi[1]);     // slots 10..19: hi again
+          *reinterpret_cast<float4*>(rowp + 3 * 32) = make_float4(hi[2], hi[3], hi[4], hi[5]);
+          *reinterpret_cast<float4*>(rowp + 4 * 32) = make_float4(hi[6], hi[7], hi[8], hi[9]);
+          *reinterpret_cast<float4*>(rowp + 5 * 32) = make_float4(lo[0], lo[1], lo[2], lo[3]);     // slots 20..29: lo
+          *reinterpret_cast<float4*>(rowp + 6 * 32) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+          *reinterpret_cast<float4*>(rowp + 7 * 32) = make_float4(lo[8], lo[9], dc, dc);           // slots 30, 31: DC
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core (async proxy) reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(0 + buf));
+    }
   } else {
     // ===================== producer: B tiles by 1-D bulk copy =====================
     if (lane == 0) {
