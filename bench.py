@@ -31,6 +31,8 @@ UNIT = "frames/s"
 CHAIN_BYTES_PER_FRAME = 128 * 64 * 4 + 256 * 4 + 16 + 16 * 4 + 64 * 4          # 34,128
 STFT_BYTES_PER_FRAME = 64 * 4 + 64 * 1024 * 4                                  # 262,400
 KERNELS_PER_STEP = 11  # look-ahead stft_plan + stft_tc_prepare (side stream), frame_chain, scan_flags, gather_rows, stft_plan, stft_tc_prepare (confirm), colstat, refine, hard, stft_tc
+KERNELS_PER_STEP_MAILBOX = 14  # the same + mailbox_post_heads, mailbox_post_max, mailbox_collect_max (N > 1, peer-memory path)
+KERNELS_PER_STEP_NCCL = 10  # no look-ahead: frame_chain, scan_flags, gather_rows, shard_pack, stft_plan, stft_tc_prepare, colstat, refine, hard, stft_tc
 
 
 def build_workload(n_frames, n_rx=3):
@@ -365,7 +367,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, cfg), "roofline": roofline, "cpu_baseline": cb,
-            "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps, "clocks": sampler.summary(),
+            "e2e": e2e, "gpu_launches": (KERNELS_PER_STEP if world == 1 else KERNELS_PER_STEP_MAILBOX if peer_mailbox else KERNELS_PER_STEP_NCCL) * args.steps, "clocks": sampler.summary(),
             "info": {k: info[k] for k in ("n_detected", "L_total", "nfft", "ncol_total", "ncol_local", "n_dtft_bins", "n_refined")}}
     if world > 1:
         line["config"]["shard_exchange"] = ("peer-memory mailboxes over NVLink (headers + max inside the kernels); NCCL for the "
