@@ -236,3 +236,32 @@ def test_mailbox_sharded_path_equals_single_gpu(split):
     for h in hs:
         h.close()
     h0.close()
+
+
+def test_mailbox_argument_errors():
+    """The mailbox entry points validate world / rank / step / pointers before anything is queued."""
+    import torch
+    from fmcw_radar_processing_b200 import FmcwError
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    case = H.make_case(n_frames=4, NTS=128, PN=64)
+    h = FmcwCuda(case["cfg"], case["calib"])
+    box = torch.zeros((h.mailbox_bytes() + 7) // 8, dtype=torch.float64, device="cuda")
+    ptrs = [box.data_ptr()]
+    with pytest.raises(FmcwError) as ei:                    # no frames processed yet
+        h.mailbox_post_heads(ptrs, 0, 1)
+    assert ei.value.status == 9
+    h.process_frames(torch.from_numpy(case["iq"]).cuda())
+    with pytest.raises(FmcwError) as ei:                    # rank >= world
+        h.mailbox_post_heads(ptrs, 1, 1)
+    assert ei.value.status == 7
+    with pytest.raises(FmcwError) as ei:                    # step numbers start at 1
+        h.mailbox_post_heads(ptrs, 0, 0)
+    assert ei.value.status == 7
+    with pytest.raises(FmcwError) as ei:                    # null mailbox
+        h.mailbox_post_heads([0], 0, 1)
+    assert ei.value.status == 2
+    with pytest.raises(FmcwError) as ei:                    # STFT before the plan
+        h.mailbox_stft(ptrs, 0, 1, torch.empty((300, 1024), dtype=torch.float32, device="cuda"))
+    assert ei.value.status == 9
+    assert h.mailbox_bytes() >= 64 * 24 + 64 * 8 * case["cfg"]["window_length"]
+    h.close()
