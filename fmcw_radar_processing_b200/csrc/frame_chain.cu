@@ -10,6 +10,8 @@
 // chirps of a warp never leave the warp) and runs the second radix-16.  Nothing of the 256 x PN
 // range cube is written to HBM (RP:207's range_tx1rx1_complete is never materialised): the slow-time
 // row of the one selected bin is re-evaluated as a single-bin DFT from the L1/L2-resident samples.
+#include <cstdlib>
+
 #include "fmcw_internal.cuh"
 
 namespace fmcw {
@@ -87,8 +89,8 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
-size_t chain_smem_bytes(uint32_t PN) {
-  size_t b = (size_t)CHAIN_WARPS * 2 * XCH_CHIRP * sizeof(float2);   // transpose slices (34,816 B)
+static size_t chain_smem_bytes_nw(uint32_t PN, int nw) {
+  size_t b = (size_t)nw * 2 * XCH_CHIRP * sizeof(float2);             // transpose slices (4,352 B per warp)
   b += 256 * sizeof(float2);                                          // tw_pair
   b += 2 * 272 * sizeof(float);                                       // skewed W_256
   b += NR * sizeof(float4);                                           // window / calibration table
@@ -99,12 +101,16 @@ size_t chain_smem_bytes(uint32_t PN) {
   b += 64 * sizeof(unsigned long long);                               // reduction scratch
   return b;
 }
+size_t chain_smem_bytes(uint32_t PN) { return chain_smem_bytes_nw(PN, CHAIN_WARPS); }
 
-template <int NZ>
-__global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const ChainParams p) {
+// NT threads per CTA (256 or 128): the smaller CTA interleaves the per-frame serial sections (peak search, Doppler
+// row) of more frames on one SM.
+template <int NZ, int NT>
+__global__ void __launch_bounds__(NT, 768 / NT) frame_chain_kernel(const ChainParams p) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* xch = reinterpret_cast<float2*>(smem_raw);
-  float2* s_twp = xch + CHAIN_WARPS * 2 * XCH_CHIRP;
+  float2* s_twp = xch + NW * 2 * XCH_CHIRP;
   float* s_twre = reinterpret_cast<float*>(s_twp + 256);
   float* s_twim = s_twre + 272;
   float4* s_win = reinterpret_cast<float4*>(s_twim + 272);
@@ -121,9 +127,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
   const int ndc = (int)min(PN, ND);
 
   // ---- tables (once per CTA; the grid is persistent over frames) ----
-  s_twp[tid] = p.tw_pair[tid];
-  for (int i = tid; i < 272; i += CHAIN_THREADS) { s_twre[i] = p.tw_re[i]; s_twim[i] = p.tw_im[i]; }
-  s_win[tid] = (tid < (int)p.nts_fft) ? p.win_tab[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 256; i += NT) s_twp[i] = p.tw_pair[i];
+  for (int i = tid; i < 272; i += NT) { s_twre[i] = p.tw_re[i]; s_twim[i] = p.tw_im[i]; }
+  for (int i = tid; i < NR; i += NT) s_win[i] = (i < (int)p.nts_fft) ? p.win_tab[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid < (int)ND) s_dtw[tid] = p.dop_tw[tid];
   if (tid < ndc) s_dwin[tid] = p.dop_win[tid];
   __syncthreads();
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
         wnext[r] = (c < PN && n < NTS) ? __ldg(cb + n) : 0u;
       }
     }
-    for (uint32_t pair = warp; pair * 2 < PN; pair += CHAIN_WARPS) {
+    for (uint32_t pair = warp; pair * 2 < PN; pair += NW) {
       const uint32_t c = pair * 2 + half;
       const bool active = c < PN;
       const uint32_t* cb = fbase + (uint64_t)(active ? c : 0) * NTS;
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
         sumQ += cq[r];
       }
       if (PF) {
-        const uint32_t cn = (pair + CHAIN_WARPS) * 2 + half;
+        const uint32_t cn = (pair + NW) * 2 + half;
         const uint32_t* cbn = fbase + (uint64_t)(cn < PN ? cn : 0) * NTS;
 #pragma unroll
         for (int r = 0; r < 4 * NZ; ++r) {
@@ -230,24 +236,26 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
       for (int k2 = 0; k2 < 16; ++k2) s_mx[warp * NR + s + 16 * k2] = mx[k2];
     }
     __syncthreads();
-    {
-      float m = s_mx[tid];
+    for (int b = tid; b < NR; b += NT) {
+      float m = s_mx[b];
 #pragma unroll
-      for (int w = 1; w < CHAIN_WARPS; ++w) m = fmaxf(m, s_mx[w * NR + tid]);
+      for (int w = 1; w < NW; ++w) m = fmaxf(m, s_mx[w * NR + b]);
       const float r = sqrtf(m);
-      s_rmax[tid] = r;
-      if (p.range_max_abs) p.range_max_abs[f * NR + tid] = r;
+      s_rmax[b] = r;
+      if (p.range_max_abs) p.range_max_abs[f * NR + b] = r;
     }
     __syncthreads();
 
     // ================= f_search_peak (RP:211; shim definition, see oracle) =================
     unsigned long long key = 0ull;
-    if (tid >= 2 && tid <= NR - 3 && tid >= p.bin_lo && tid <= p.bin_hi) {
-      const float fp = s_rmax[tid];
-      if (fp >= p.range_thr && fp >= s_rmax[tid - 2] && fp >= s_rmax[tid - 1] && fp > s_rmax[tid + 1] &&
-          fp > s_rmax[tid + 2]) {
-        const unsigned long long lo = 0xffffffffull - (unsigned)tid;
-        key = (p.peak_mode == 0) ? (((unsigned long long)__float_as_uint(fp) << 32) | lo) : ((1ull << 32) | lo);
+    for (int b = tid; b < NR; b += NT) {
+      if (b >= 2 && b <= NR - 3 && b >= p.bin_lo && b <= p.bin_hi) {
+        const float fp = s_rmax[b];
+        if (fp >= p.range_thr && fp >= s_rmax[b - 2] && fp >= s_rmax[b - 1] && fp > s_rmax[b + 1] && fp > s_rmax[b + 2]) {
+          const unsigned long long lo = 0xffffffffull - (unsigned)b;
+          const unsigned long long kb = (p.peak_mode == 0) ? (((unsigned long long)__float_as_uint(fp) << 32) | lo) : ((1ull << 32) | lo);
+          key = kb > key ? kb : key;
+        }
       }
     }
 #pragma unroll
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
     __syncthreads();
     key = s_red[0];
 #pragma unroll
-    for (int w = 1; w < CHAIN_WARPS; ++w) key = s_red[w] > key ? s_red[w] : key;
+    for (int w = 1; w < NW; ++w) key = s_red[w] > key ? s_red[w] : key;
     const bool det = key != 0ull;
     const int kbin = det ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : -1;
     __syncthreads();   // s_red is reused below
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
       if (p.range_mag) p.range_mag[f] = det ? s_rmax[kbin] : 0.f;
     }
     if (!det) {
-      for (uint32_t c = tid; c < PN; c += CHAIN_THREADS) { p.slow64[f * PN + c] = 0.0; if (p.slow_mag) p.slow_mag[f * PN + c] = 0.f; }
+      for (uint32_t c = tid; c < PN; c += NT) { p.slow64[f * PN + c] = 0.0; if (p.slow_mag) p.slow_mag[f * PN + c] = 0.f; }
       if (p.doppler_row && tid < (int)ND) p.doppler_row[f * ND + tid] = make_float2(0.f, 0.f);
       if (p.doppler_bin && tid == 0) p.doppler_bin[f] = (int)ND / 2;
       continue;
@@ -281,12 +289,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
     double2* s_h = reinterpret_cast<double2*>(xch) + NR;     // [CHAIN_WARPS]
     {
       double hr = 0.0, hi = 0.0;
-      if (tid < (int)p.nts_fft) {
-        const double gw = p.win_tab_d[3 * tid], h_re = p.win_tab_d[3 * tid + 1], h_im = p.win_tab_d[3 * tid + 2];
-        const double2 tw = p.tw_d[((uint32_t)tid * (uint32_t)kbin) & (NR - 1)];
-        s_G[tid] = make_double2(gw * tw.x, gw * tw.y);
-        hr = h_re * tw.x - h_im * tw.y;
-        hi = h_re * tw.y + h_im * tw.x;
+      for (int n = tid; n < (int)p.nts_fft; n += NT) {
+        const double gw = p.win_tab_d[3 * n], h_re = p.win_tab_d[3 * n + 1], h_im = p.win_tab_d[3 * n + 2];
+        const double2 tw = p.tw_d[((uint32_t)n * (uint32_t)kbin) & (NR - 1)];
+        s_G[n] = make_double2(gw * tw.x, gw * tw.y);
+        hr += h_re * tw.x - h_im * tw.y;
+        hi += h_re * tw.y + h_im * tw.x;
       }
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
@@ -299,10 +307,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
     {
       double Hr = 0.0, Hi = 0.0;
 #pragma unroll
-      for (int w = 0; w < CHAIN_WARPS; ++w) { Hr += s_h[w].x; Hi += s_h[w].y; }
+      for (int w = 0; w < NW; ++w) { Hr += s_h[w].x; Hi += s_h[w].y; }
       // eight lanes per chirp, four chirps per warp
       const int grp = lane >> 3, j8 = lane & 7;
-      for (uint32_t c0 = warp * 4; c0 < PN; c0 += CHAIN_WARPS * 4) {
+      for (uint32_t c0 = warp * 4; c0 < PN; c0 += NW * 4) {
         const uint32_t c = c0 + grp;
         const bool live = c < PN;
         const uint32_t* cb = fbase + (uint64_t)(live ? c : 0) * NTS;
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
 
     // mean over all PN chirps (RP:217)
     float sr = 0.f, si = 0.f;
-    for (uint32_t c = tid; c < PN; c += CHAIN_THREADS) {
+    for (uint32_t c = tid; c < PN; c += NT) {
       const float2 r = s_row[c];
       sr += r.x;
       si += r.y;
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
     __syncthreads();
     float mr = 0.f, mi = 0.f;
 #pragma unroll
-    for (int w = 0; w < CHAIN_WARPS; ++w) { mr += s_sum[w].x; mi += s_sum[w].y; }
+    for (int w = 0; w < NW; ++w) { mr += s_sum[w].x; mi += s_sum[w].y; }
     mr /= (float)PN;
     mi /= (float)PN;
     __syncthreads();
@@ -389,26 +397,33 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 3) frame_chain_kernel(const Cha
   }
 }
 
+template <int NZ, int NT>
+static cudaError_t launch_chain_variant(const ChainParams& p, int sms, cudaStream_t st) {
+  const size_t smem = chain_smem_bytes_nw(p.PN, NT / 32);
+  const uint64_t max_grid = (uint64_t)sms * (768 / NT) * 8;   // persistent over frames; tables are loaded once per CTA
+  const unsigned grid = (unsigned)(p.n_frames < max_grid ? p.n_frames : max_grid);
+  cudaError_t e = cudaFuncSetAttribute(frame_chain_kernel<NZ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  frame_chain_kernel<NZ, NT><<<grid, NT, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st) {
   if (p.n_frames == 0) return cudaSuccess;
-  const size_t smem = chain_smem_bytes(p.PN);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint64_t max_grid = (uint64_t)sms * 3 * 8;   // persistent over frames; tables are loaded once per CTA
-  const unsigned grid = (unsigned)(p.n_frames < max_grid ? p.n_frames : max_grid);
-  cudaError_t e;
-#define FMCW_LAUNCH_CHAIN(NZ)                                                                              \
-  do {                                                                                                     \
-    e = cudaFuncSetAttribute(frame_chain_kernel<NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                        \
-    frame_chain_kernel<NZ><<<grid, CHAIN_THREADS, smem, st>>>(p);                                          \
+  static int nt = 0;
+  if (!nt) { const char* v = getenv("FMCW_CHAIN_THREADS"); const int r = v ? atoi(v) : 0; nt = (r == 256) ? 256 : 128; }   // 128 measured fastest (64 / 96 / 128 / 256: 0.192 / 0.186 / 0.185 / 0.199 ms on C2)
+#define FMCW_CHAIN_NT(NT)                                                  \
+  do {                                                                     \
+    if (p.nts_fft <= 64) return launch_chain_variant<1, NT>(p, sms, st);   \
+    if (p.nts_fft <= 128) return launch_chain_variant<2, NT>(p, sms, st);  \
+    return launch_chain_variant<4, NT>(p, sms, st);                        \
   } while (0)
-  if (p.nts_fft <= 64) FMCW_LAUNCH_CHAIN(1);
-  else if (p.nts_fft <= 128) FMCW_LAUNCH_CHAIN(2);
-  else FMCW_LAUNCH_CHAIN(4);
-#undef FMCW_LAUNCH_CHAIN
-  return cudaGetLastError();
+  if (nt == 256) FMCW_CHAIN_NT(256);
+  FMCW_CHAIN_NT(128);
+#undef FMCW_CHAIN_NT
 }
 
 }  // namespace fmcw
