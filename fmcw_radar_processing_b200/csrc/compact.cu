@@ -54,7 +54,54 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const sig_t* __restric
   }
 }
 
+// Recordings of up to COMPACT_FUSED_MAX frames: one launch.  A CTA owns 32 frames; it counts the detections before
+// its first frame itself (n_frames * 4 B of flags are L2 resident), ranks its own frames with a ballot and copies
+// their rows; the CTA of the last frames publishes the total.
+constexpr uint64_t COMPACT_FUSED_MAX = 16384;
+constexpr int COMPACT_FPB = 32;
+
+__global__ void __launch_bounds__(256) compact_fused_kernel(const int32_t* __restrict__ det, uint64_t n_frames, uint32_t PN,
+                                                            const sig_t* __restrict__ slow_mag, sig_t* __restrict__ xc,
+                                                            unsigned long long* __restrict__ n_det) {
+  __shared__ unsigned s_cnt[8];
+  __shared__ unsigned s_before, s_ballot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t f0 = (uint64_t)blockIdx.x * COMPACT_FPB;
+  unsigned cnt = 0;
+  for (uint64_t i = tid; i < f0; i += 256) cnt += det[i] != 0 ? 1u : 0u;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+  if (lane == 0) s_cnt[warp] = cnt;
+  if (warp == 0) {
+    const uint64_t f = f0 + lane;
+    const unsigned b = __ballot_sync(0xffffffffu, f < n_frames && det[f] != 0);
+    if (lane == 0) s_ballot = b;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += s_cnt[w];
+    s_before = t;
+    if (f0 + COMPACT_FPB >= n_frames) *n_det = (unsigned long long)t + __popc(s_ballot);
+  }
+  __syncthreads();
+  const unsigned before = s_before, ballot = s_ballot;
+  for (uint32_t i = tid; i < COMPACT_FPB * PN; i += 256) {
+    const uint32_t j = i / PN, c = i - j * PN;
+    if (ballot & (1u << j)) {
+      const unsigned k = before + __popc(ballot & ((1u << j) - 1u));
+      xc[(uint64_t)k * PN + c] = slow_mag[(f0 + j) * PN + c];
+    }
+  }
+}
+
 cudaError_t launch_compact(const CompactParams& p, cudaStream_t st) {
+  if (p.n_frames > 0 && p.n_frames <= COMPACT_FUSED_MAX) {
+    const unsigned blocks = (unsigned)((p.n_frames + COMPACT_FPB - 1) / COMPACT_FPB);
+    compact_fused_kernel<<<blocks, 256, 0, st>>>(p.detected, p.n_frames, p.PN, p.slow_mag, p.xc, p.n_det);
+    return cudaGetLastError();
+  }
+
   scan_flags_kernel<<<1, 1024, 0, st>>>(p.detected, p.n_frames, p.det_list, p.n_det);
   const uint64_t total = p.n_frames * p.PN;
   uint64_t blocks = (total + 255) / 256;
