@@ -30,9 +30,9 @@ UNIT = "frames/s"
 # algorithmic bytes per frame of the C1/C2 shape (1 processed RX, 64 x 128, hop 1)
 CHAIN_BYTES_PER_FRAME = 128 * 64 * 4 + 256 * 4 + 16 + 16 * 4 + 64 * 4          # 34,128
 STFT_BYTES_PER_FRAME = 64 * 4 + 64 * 1024 * 4                                  # 262,400
-KERNELS_PER_STEP = 11  # look-ahead stft_plan + stft_tc_prepare (side stream), frame_chain, scan_flags, gather_rows, stft_plan, stft_tc_prepare (confirm), colstat, refine, hard, stft_tc
-KERNELS_PER_STEP_MAILBOX = 14  # the same + mailbox_post_heads, mailbox_post_max, mailbox_collect_max (N > 1, peer-memory path)
-KERNELS_PER_STEP_NCCL = 10  # no look-ahead: frame_chain, scan_flags, gather_rows, shard_pack, stft_plan, stft_tc_prepare, colstat, refine, hard, stft_tc
+KERNELS_PER_STEP = 10  # look-ahead stft_plan + stft_tc_prepare (side stream), frame_chain, compact_fused, stft_plan, stft_tc_prepare (confirm), colstat, refine, hard, stft_tc
+KERNELS_PER_STEP_MAILBOX = 13  # the same + mailbox_post_heads, mailbox_post_max, mailbox_collect_max (N > 1, peer-memory path)
+KERNELS_PER_STEP_NCCL = 9  # no look-ahead: frame_chain, compact_fused, shard_pack, stft_plan, stft_tc_prepare, colstat, refine, hard, stft_tc
 
 
 def build_workload(n_frames, n_rx=3):
