@@ -53,3 +53,35 @@ for name, n, n_rx, PN, NTS, win, ov, scene in CASES:
     h.close()
     del iq, out, inten
     torch.cuda.empty_cache()
+
+# ---- C5 fleet: many independent radars (C1 shape, 500 frames each) on one GPU ----
+import time
+from fmcw_radar_processing_b200.fleet import Fleet
+
+n_radars, n, n_rx, PN, NTS = 64, 500, 1, 64, 128
+sx = make_sxml(numSamplesPerChirp=NTS, numChirpsPerFrame=PN, numAntennasRx=n_rx)
+cfg = fmcw_configurations(sx)
+calib = synth.default_calib(n_rx, NTS) / 4095.0
+gen = FmcwCuda(cfg, calib, torch_stream_sync=False)
+recs = []
+for r in range(n_radars):
+    scene = synth.scene_c1(1000 + r)
+    tab = synth.scene_tables(scene, cfg["dist_per_bin"], 256, cfg["PRT"], cfg["lambda"], 0, n)
+    iq = torch.empty((n, n_rx, PN, NTS, 2), dtype=torch.int16, device=dev)
+    gen.synth_frames(tab, scene.seed, 0, out=iq)
+    recs.append(iq)
+gen.synchronize()
+gen.close()
+for nh in (1, 4, 8):
+    fleet = Fleet(cfg, calib, n_handles=nh)
+    fleet.run(recs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    K = 3
+    for _ in range(K):
+        res = fleet.run(recs)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / K
+    print(f"C5 fleet, {n_radars} radars x {n} frames, {nh} handle(s) in flight: {n_radars * n / dt:12.0f} frames/s  "
+          f"{dt * 1e3:8.3f} ms per fleet pass (host wall clock)")
+    fleet.close()

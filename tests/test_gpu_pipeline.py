@@ -265,3 +265,32 @@ def test_mailbox_argument_errors():
     assert ei.value.status == 9
     assert h.mailbox_bytes() >= 64 * 24 + 64 * 8 * case["cfg"]["window_length"]
     h.close()
+
+
+def test_fleet_of_radars_equals_one_by_one():
+    """C5: independent radars through a pool of handles on concurrent streams give, radar by radar, exactly what a
+    single handle gives (own nfft, own maximum; recordings of different lengths, one without any target)."""
+    import torch
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    from fmcw_radar_processing_b200.fleet import Fleet
+    cases = [H.make_case(n_frames=n, NTS=128, PN=64, seed=100 + i) for i, n in enumerate((12, 30, 7, 21, 16, 9))]
+    cases[2]["iq"][:] = 2048                                   # a radar that never detects anything
+    cfg, calib = cases[0]["cfg"], cases[0]["calib"]
+    recs = [torch.from_numpy(c["iq"]).cuda() for c in cases]
+    fleet = Fleet(cfg, calib, n_handles=3)
+    got = fleet.run(recs)
+    h = FmcwCuda(cfg, calib)
+    for i, rec in enumerate(recs):
+        out, inten = h.run(rec)
+        info = h.info()
+        g = got[i]
+        assert g["info"]["n_detected"] == info["n_detected"] and g["info"]["nfft"] == info["nfft"]
+        assert g["info"]["pmax_raw"] == info["pmax_raw"] and g["ncol"] == info["ncol_local"]
+        for k in ("detected", "range_bin", "doppler_bin", "range_mag", "range_max_abs"):
+            assert torch.equal(g[k], out[k]), k
+        n = info["ncol_local"]
+        a, b = g["intensity"][:n], inten[:n]
+        assert torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
+    assert got[2]["info"]["n_detected"] == 0 and got[2]["ncol"] == 0
+    h.close()
+    fleet.close()
