@@ -129,6 +129,12 @@ struct fmcw_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool lookahead = false;     // a look-ahead plan is in flight on the side stream (ev_join)
   uint32_t mb_world = 0, mb_rank = 0;   // mailbox path: layout of the last pass (assumed again by the look-ahead plan)
+  // the five small launches between compaction and the main STFT kernel (plan confirm, operand prepare, colstat,
+  // refine, hard) replayed as one CUDA graph: their cost is launch latency, not work
+  cudaGraphExec_t mx_exec = nullptr;
+  StftTables mx_key_tables{};
+  const void* mx_key_xc = nullptr;
+  int mx_eligible_calls = 0;
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   std::string err;
   // chain tables
@@ -366,11 +372,32 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
   if (!h->planned) {
     int spec_mode = 0;
     CK(join_lookahead(h, spec_mode), "join look-ahead plan");
-    CK(launch_stft_plan(h->st, h->geom, from_device_count ? h->ndet.as<unsigned long long>() : nullptr,
-                        h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks, h->stream,
-                        nullptr, 0, 0, nullptr, spec_mode), "stft plan kernel");
+    static int use_graph = -1;
+    if (use_graph < 0) { const char* v = getenv("FMCW_GRAPH"); use_graph = (v && atoi(v) == 0) ? 0 : 1; }
+    const bool graphable = use_graph && from_device_count && compute_max && spec_mode == 2 && ++h->mx_eligible_calls > 1;
+    if (graphable) {
+      if (!h->mx_exec || memcmp(&h->mx_key_tables, &h->st, sizeof(StftTables)) != 0 || h->mx_key_xc != h->xc.p) {
+        if (h->mx_exec) { cudaGraphExecDestroy(h->mx_exec); h->mx_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
+        cudaError_t e1 = launch_stft_plan(h->st, h->geom, h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame, 0, 0, 0,
+                                          0, h->n_chunks, h->stream, nullptr, 0, 0, nullptr, 2);
+        cudaError_t e2 = launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream);
+        cudaError_t e3 = cudaStreamEndCapture(h->stream, &graph);
+        CK(e1, "capture stft plan"); CK(e2, "capture stft max"); CK(e3, "end capture");
+        cudaError_t e4 = cudaGraphInstantiate(&h->mx_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CK(e4, "instantiate graph");
+        h->mx_key_tables = h->st; h->mx_key_xc = h->xc.p;
+      }
+      CK(cudaGraphLaunch(h->mx_exec, h->stream), "launch plan + max graph");
+    } else {
+      CK(launch_stft_plan(h->st, h->geom, from_device_count ? h->ndet.as<unsigned long long>() : nullptr,
+                          h->cfg.num_chirps_per_frame, L_total, offset, L_local, L_avail, h->n_chunks, h->stream,
+                          nullptr, 0, 0, nullptr, spec_mode), "stft plan kernel");
+      if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream), "stft max kernels");
+    }
     h->planned = true; h->plan_L = L_total; h->plan_off = offset; h->plan_avail = L_avail;
-    if (compute_max) CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream), "stft max kernels");
   }
   if (!compute_max) CK(launch_stft_set_max(h->st, pmax_override, h->stream), "stft set max");
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
@@ -574,6 +601,7 @@ void fmcw_destroy(fmcw_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->side) cudaStreamSynchronize(h->side);
+  if (h->mx_exec) { cudaGraphExecDestroy(h->mx_exec); h->mx_exec = nullptr; }
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
