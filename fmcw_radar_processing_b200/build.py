@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfmcw_cuda.so")
-SOURCES = ["capi.cu", "frame_chain.cu", "compact.cu", "stft.cu", "stft_tc.cu", "mailbox.cu", "synth.cu", "json_writer.cu"]
+SOURCES = ["capi.cu", "frame_chain.cu", "frame_chain_warp.cu", "compact.cu", "stft.cu", "stft_tc.cu", "mailbox.cu", "synth.cu", "json_writer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math=false"]
 

@@ -138,7 +138,7 @@ struct fmcw_handle {
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   std::string err;
   // chain tables
-  DevBuf win_tab, win_tab_d, tw_d, tw_pair, tw_re, tw_im, dop_tw, dop_win;
+  DevBuf win_tab, win_tab_d, tw_d, hfft_d, tw_pair, tw_re, tw_im, dop_tw, dop_win;
   int bin_lo = 0, bin_hi = -1;
   // STFT tables
   StftTables st{};
@@ -294,7 +294,7 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   p.iq = d_iq; p.n_frames = n_frames; p.NTS = NTS; p.PN = PN; p.n_rx = n_rx; p.rx_sel = rx_sel; p.ND = ND;
   p.nts_fft = NTS < (uint32_t)NR ? NTS : (uint32_t)NR;
   p.win_tab = h->win_tab.as<float4>(); p.tw_pair = h->tw_pair.as<float2>();
-  p.win_tab_d = h->win_tab_d.as<double>(); p.tw_d = h->tw_d.as<double2>();
+  p.win_tab_d = h->win_tab_d.as<double>(); p.tw_d = h->tw_d.as<double2>(); p.hfft_d = h->hfft_d.as<double2>();
   p.tw_re = h->tw_re.as<float>(); p.tw_im = h->tw_im.as<float>();
   p.dop_tw = h->dop_tw.as<float2>(); p.dop_win = h->dop_win.as<float>();
   p.bin_lo = h->bin_lo; p.bin_hi = h->bin_hi;
@@ -514,6 +514,16 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
     const double a = -2.0 * M_PI * (double)k / NR;
     twd[k] = make_double2(std::cos(a), std::sin(a));
   }
+  std::vector<double2> hfft(NR);      // H[k] = sum_n h[n] W^(n k): the calibration term of the slow-time row at bin k
+  for (int k = 0; k < NR; ++k) {
+    double hr = 0.0, hi = 0.0;
+    for (uint32_t n = 0; n < nts_fft; ++n) {
+      const double2 tw = twd[((uint32_t)n * (uint32_t)k) & (NR - 1)];
+      hr += wtd[3 * n + 1] * tw.x - wtd[3 * n + 2] * tw.y;
+      hi += wtd[3 * n + 1] * tw.y + wtd[3 * n + 2] * tw.x;
+    }
+    hfft[k] = make_double2(hr, hi);
+  }
   std::vector<float2> twp(256);
   for (int k1 = 0; k1 < 16; ++k1)
     for (int s = 0; s < 16; ++s) {
@@ -572,7 +582,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   ok(upload(h->win_tab, wt, h->stream)); ok(upload(h->tw_pair, twp, h->stream));
-  ok(upload(h->win_tab_d, wtd, h->stream)); ok(upload(h->tw_d, twd, h->stream));
+  ok(upload(h->win_tab_d, wtd, h->stream)); ok(upload(h->tw_d, twd, h->stream)); ok(upload(h->hfft_d, hfft, h->stream));
   ok(upload(h->tw_re, twre, h->stream)); ok(upload(h->tw_im, twim, h->stream));
   ok(upload(h->dop_tw, dtw, h->stream)); ok(upload(h->dop_win, dwin, h->stream));
   ok(upload(h->swin, swin, h->stream));
@@ -604,7 +614,7 @@ void fmcw_destroy(fmcw_handle* h) {
   if (h->mx_exec) { cudaGraphExecDestroy(h->mx_exec); h->mx_exec = nullptr; }
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
-                   &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
+                   &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->hfft_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
                    &h->synth_tab, &h->tcb, &h->colub};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
@@ -1002,7 +1012,7 @@ fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_fr
   p.n_rx = c.num_Rx_antennas; p.rx_sel = c.rx_select; p.ND = c.Doppler_fft_size;
   p.nts_fft = p.NTS < (uint32_t)NR ? p.NTS : (uint32_t)NR;
   p.win_tab = h->win_tab.as<float4>(); p.tw_pair = h->tw_pair.as<float2>();
-  p.win_tab_d = h->win_tab_d.as<double>(); p.tw_d = h->tw_d.as<double2>();
+  p.win_tab_d = h->win_tab_d.as<double>(); p.tw_d = h->tw_d.as<double2>(); p.hfft_d = h->hfft_d.as<double2>();
   p.tw_re = h->tw_re.as<float>(); p.tw_im = h->tw_im.as<float>();
   p.dop_tw = h->dop_tw.as<float2>(); p.dop_win = h->dop_win.as<float>();
   CK(h->o_slow64.ensure((size_t)c.num_chirps_per_frame * sizeof(sig_t)), "alloc");

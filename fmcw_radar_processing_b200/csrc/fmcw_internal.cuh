@@ -25,6 +25,7 @@ struct ChainParams {
   const float4* win_tab;     // [nts_fft] {gw, h_re, h_im, 0}: xw = gw*(NTS*code - sum) - h
   const double* win_tab_d;   // [nts_fft][3] the same table in float64 (slow-time row)
   const double2* tw_d;       // [256] W_256^k in float64
+  const double2* hfft_d;     // [256] FFT of the calibration term h[n] (float64), subtracted from the slow-time row
   const float2* tw_pair;     // [16][16] W_256^(s*k1)
   const float*  tw_re;       // [272] skewed W_256^k table (index k + k/16)
   const float*  tw_im;
@@ -43,6 +44,9 @@ struct ChainParams {
 
 size_t chain_smem_bytes(uint32_t PN);
 cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st);
+// one warp per frame, two chirps per lane (frame_chain_warp.cu); launch_frame_chain dispatches to it when supported
+bool chain_warp_supported(const ChainParams& p);
+cudaError_t launch_frame_chain_warp(const ChainParams& p, cudaStream_t st);
 
 // ---- compaction of the detected frames' slow-time rows (RP:257-260) ------------------------------
 struct CompactParams {

@@ -412,6 +412,9 @@ static cudaError_t launch_chain_variant(const ChainParams& p, int sms, cudaStrea
 
 cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st) {
   if (p.n_frames == 0) return cudaSuccess;
+  static int variant = -1;   // FMCW_CHAIN_VARIANT=0: the one-CTA-per-frame kernel below (kept for A/B runs and odd shapes)
+  if (variant < 0) { const char* v = getenv("FMCW_CHAIN_VARIANT"); variant = (v && atoi(v) == 0) ? 0 : 1; }
+  if (variant == 1 && chain_warp_supported(p)) return launch_frame_chain_warp(p, st);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
