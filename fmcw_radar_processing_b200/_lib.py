@@ -14,6 +14,7 @@ STATUS_NAMES = {0: "FMCW_OK", 1: "FMCW_ERR_CONFIG", 2: "FMCW_ERR_POINTER", 3: "F
 PEAK_STRONGEST, PEAK_FIRST = 0, 1
 LAYOUT_TIME_MAJOR, LAYOUT_FREQ_MAJOR = 0, 1
 OPT_ASYNC_HOST = 1
+OPT_STFT_PRECISION = 2      # 0: tensor-core TF32 x 2 kernel (default), 1: float64 kernel
 
 
 class FmcwError(RuntimeError):

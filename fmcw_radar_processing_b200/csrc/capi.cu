@@ -143,7 +143,7 @@ struct fmcw_handle {
   // STFT tables
   StftTables st{};
   StftGeom geom{};
-  DevBuf plan, bins, kcb, wdc, qpos, aq, qend, coef, swin, hard, derr, gmax;
+  DevBuf plan, bins, kcb, wdc, qpos, aq, qend, coef, swin, swin_d, hard, derr, gmax;
   // scratch
   DevBuf tcb, colub;
   DevBuf iq_stage, o_rmax, o_det, o_rbin, o_rmag, o_dbin, o_drow, o_slow, o_slow64, f32_stage, xc, det_list, ndet, inten, synth_tab;
@@ -154,6 +154,7 @@ struct fmcw_handle {
   uint64_t plan_L = 0, plan_off = 0, plan_avail = 0;
   StftPlan plan_host{};
   int n_chunks = 12;
+  int stft_precise = 0;      // FMCW_OPT_STFT_PRECISION: 1 = float64 STFT kernel
   bool async_host = false;   // FMCW_OPT_ASYNC_HOST: calls with (pinned) host buffers return after enqueueing
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, chain, compact, plan+max, main
   bool ev_valid[5] = {false, false, false, false, false};
@@ -218,6 +219,7 @@ void fill_tables(fmcw_handle* h) {
   h->st.qend = h->qend.as<int>();
   h->st.coef = h->coef.as<float>();
   h->st.win = h->swin.as<float>();
+  h->st.win_d = h->swin_d.as<double>();
   h->st.hard_list = h->hard.as<unsigned int>();
   h->st.tcB = h->tcb.as<float>();
 }
@@ -401,8 +403,8 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
   }
   if (!compute_max) CK(launch_stft_set_max(h->st, pmax_override, h->stream), "stft set max");
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
-  CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), d_out, cap, d_ld, (int)sout->layout, h->derr.as<int>(), h->stream),
-     "stft main kernel");
+  CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), d_out, cap, d_ld, (int)sout->layout, h->derr.as<int>(), h->stream,
+                      nullptr, h->stft_precise), "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
   if (!dev_out && h->async_host) {
@@ -585,7 +587,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   ok(upload(h->win_tab_d, wtd, h->stream)); ok(upload(h->tw_d, twd, h->stream)); ok(upload(h->hfft_d, hfft, h->stream));
   ok(upload(h->tw_re, twre, h->stream)); ok(upload(h->tw_im, twim, h->stream));
   ok(upload(h->dop_tw, dtw, h->stream)); ok(upload(h->dop_win, dwin, h->stream));
-  ok(upload(h->swin, swin, h->stream));
+  ok(upload(h->swin, swin, h->stream)); ok(upload(h->swin_d, wk, h->stream));
   ok(h->plan.ensure(sizeof(StftPlan))); ok(h->bins.ensure((size_t)nb_max * 4)); ok(h->kcb.ensure((size_t)nb_max * 4)); ok(h->wdc.ensure((size_t)nb_max * 4));
   ok(h->qpos.ensure(MAX_NQ * 4)); ok(h->aq.ensure(MAX_NQ * 4)); ok(h->qend.ensure((size_t)(nb_max + 2) * 4));
   ok(h->coef.ensure((size_t)nb_max * 2 * half * 4 + 64));
@@ -613,7 +615,7 @@ void fmcw_destroy(fmcw_handle* h) {
   if (h->side) cudaStreamSynchronize(h->side);
   if (h->mx_exec) { cudaGraphExecDestroy(h->mx_exec); h->mx_exec = nullptr; }
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
-                   &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
+                   &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->swin_d, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->hfft_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
                    &h->synth_tab, &h->tcb, &h->colub};
   for (DevBuf* b : all) b->release();
@@ -700,6 +702,9 @@ fmcw_status fmcw_set_option(fmcw_handle* h, int option, int64_t value) {
   if (!g.ok) return FMCW_ERR_BUSY;
   switch (option) {
     case FMCW_OPT_ASYNC_HOST: h->async_host = value != 0; return FMCW_OK;
+    case FMCW_OPT_STFT_PRECISION:
+      if (value != 0 && value != 1) return fail(h, FMCW_ERR_CONFIG, "FMCW_OPT_STFT_PRECISION takes 0 (fast) or 1 (float64)");
+      h->stft_precise = (int)value; return FMCW_OK;
     default: return fail(h, FMCW_ERR_CONFIG, "unknown option");
   }
 }
@@ -885,7 +890,7 @@ fmcw_status fmcw_shard_stft(fmcw_handle* h, const double* global_max_dev, const 
   const uint64_t ld = sout->ld_cols ? sout->ld_cols : sout->capacity_cols;
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
   CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
-                      h->derr.as<int>(), h->stream, global_max_dev), "stft main kernel");
+                      h->derr.as<int>(), h->stream, global_max_dev, h->stft_precise), "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
   return FMCW_OK;
@@ -958,7 +963,7 @@ fmcw_status fmcw_mailbox_stft(fmcw_handle* h, void* const* mailboxes, uint32_t w
      "mailbox collect max kernel");
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
   CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
-                      h->derr.as<int>(), h->stream, h->gmax.as<double>() + 1), "stft main kernel");
+                      h->derr.as<int>(), h->stream, h->gmax.as<double>() + 1, h->stft_precise), "stft main kernel");
   CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
   h->have_info = false;
   return FMCW_OK;

@@ -79,6 +79,7 @@ struct StftTables {             // device arrays owned by the handle
   int* qend;                    // [nb_max+1] queries [qend[p-1], qend[p]) complete when position p is known
   float* coef;                  // [nb_max][2*half] cos((m+d)w), sin((m+d)w)
   float* win;                   // [win] kaiser window (host computed, float64 -> float32)
+  double* win_d;                // [win] the same window in float64 (DC response tables, float64 STFT kernel)
   float* wdc;                   // [nb_max] window DC response per bin position (generic-window kernel)
   unsigned int* hard_list;      // columns whose max needs the exhaustive search
   unsigned int hard_cap;
@@ -109,7 +110,7 @@ cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const sig_t*
 cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout,
-                             int* d_err, cudaStream_t st, const double* gmax_dev = nullptr);
+                             int* d_err, cudaStream_t st, const double* gmax_dev = nullptr, int precise = 0);
 
 // tensor-core (tcgen05) STFT main kernel, window_length = 20 (stft_tc.cu)
 size_t stft_tc_table_bytes(int nb_max);

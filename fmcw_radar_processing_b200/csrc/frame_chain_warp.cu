@@ -108,7 +108,6 @@ __device__ __forceinline__ void dft16(cx2 (&v)[16]) {
     for (int b = a + 1; b < 4; ++b) { const cx2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
 }
 
-constexpr int WF_WARPS = 4;                      // warps (= frames in flight) per CTA
 
 constexpr int WF_XROW = 17;                      // float4 stride between rows of the in-warp transpose
 constexpr int WF_XHALF = 16 * WF_XROW;           // float4 per half-warp slice (two chirps)
@@ -117,7 +116,7 @@ struct WarpSmem {                                // byte offsets inside the dyna
   int tw, wg, wh, dtw, dwin, per_warp0, per_warp;
   int xch, rmax, csum, row, total;
 };
-__host__ __device__ inline WarpSmem warp_smem_layout(uint32_t PN) {
+__host__ __device__ inline WarpSmem warp_smem_layout(uint32_t PN, int WF_WARPS) {
   WarpSmem L;
   int o = 0;
   L.tw = o;   o += 15 * 16 * (int)sizeof(float4);          // (c, c, s, s) of W256^(s*k1), k1 = 1..15
@@ -139,11 +138,11 @@ __host__ __device__ inline WarpSmem warp_smem_layout(uint32_t PN) {
 }
 
 // EXACT: NTS == 64*NZ and PN % 4 == 0 and no range-spectrum export: no predicates anywhere in pass 1.
-template <int NZ, bool EXACT, int MINB>
+template <int NZ, bool EXACT, int MINB, int WF_WARPS>
 __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t NTS = p.NTS, PN = p.PN, ND = p.ND;
-  const WarpSmem L = warp_smem_layout(PN);
+  const WarpSmem L = warp_smem_layout(PN, WF_WARPS);
   float4* s_tw = reinterpret_cast<float4*>(smem_raw + L.tw);
   float2* s_wg = reinterpret_cast<float2*>(smem_raw + L.wg);
   float4* s_wh = reinterpret_cast<float4*>(smem_raw + L.wh);
@@ -189,7 +188,7 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
     for (int i = 0; i < 16; ++i) mx[i] = 0.f;
 
     // ================= pass 1: range FFT of every chirp, running max of |X|^2 =================
-    constexpr bool PF = (NZ <= 2);       // software pipelining: the next quad's samples are requested before this FFT
+    constexpr bool PF = (NZ <= 2) && (MINB <= 3);       // software pipelining: the next quad's samples are requested before this FFT
     uint32_t wa[4 * NZ], wb[4 * NZ];
     auto load_quad = [&](uint32_t q) {
       const uint32_t ca = 4 * q + half, cb = ca + 2;
@@ -479,16 +478,16 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
   }
 }
 
-template <int NZ, bool EXACT, int MINB>
+template <int NZ, bool EXACT, int MINB, int WF_WARPS = 4>
 cudaError_t launch_variant(const ChainParams& p, int sms, cudaStream_t st) {
-  const WarpSmem L = warp_smem_layout(p.PN);
+  const WarpSmem L = warp_smem_layout(p.PN, WF_WARPS);
   const int per_sm = MINB;
   const uint64_t ctas_needed = (p.n_frames + WF_WARPS - 1) / WF_WARPS;
   const uint64_t max_grid = (uint64_t)sms * per_sm;
   const unsigned grid = (unsigned)(ctas_needed < max_grid ? ctas_needed : max_grid);
-  cudaError_t e = cudaFuncSetAttribute(frame_chain_warp_kernel<NZ, EXACT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  cudaError_t e = cudaFuncSetAttribute(frame_chain_warp_kernel<NZ, EXACT, MINB, WF_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return e;
-  frame_chain_warp_kernel<NZ, EXACT, MINB><<<grid, WF_WARPS * 32, L.total, st>>>(p);
+  frame_chain_warp_kernel<NZ, EXACT, MINB, WF_WARPS><<<grid, WF_WARPS * 32, L.total, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -496,7 +495,7 @@ cudaError_t launch_variant(const ChainParams& p, int sms, cudaStream_t st) {
 
 bool chain_warp_supported(const ChainParams& p) {
   // float holds NTS*code - sum exactly while NTS * 32768 < 2^24; the per-warp shared memory grows with PN
-  return p.NTS <= 511 && p.PN <= 1024 && warp_smem_layout(p.PN).total <= 100 * 1024;
+  return p.NTS <= 511 && p.PN <= 1024 && warp_smem_layout(p.PN, 4).total <= 100 * 1024;
 }
 
 cudaError_t launch_frame_chain_warp(const ChainParams& p, cudaStream_t st) {
@@ -513,6 +512,11 @@ cudaError_t launch_frame_chain_warp(const ChainParams& p, cudaStream_t st) {
       return exact ? launch_variant<NZ_, true, (NZ_ == 4 ? 3 : 4)>(p, sms, st) : launch_variant<NZ_, false, (NZ_ == 4 ? 3 : 4)>(p, sms, st); \
     return exact ? launch_variant<NZ_, true, 3>(p, sms, st) : launch_variant<NZ_, false, 3>(p, sms, st);    \
   } while (0)
+  static int nwarps = 0;
+  if (!nwarps) { const char* v = getenv("FMCW_CHAIN_WARPS"); nwarps = v ? atoi(v) : 4; }
+  if (nz == 2 && exact && nwarps == 5) return launch_variant<2, true, 3, 5>(p, sms, st);
+  if (nz == 2 && exact && nwarps == 6) return launch_variant<2, true, 3, 6>(p, sms, st);
+  if (nz == 2 && exact && nwarps == 8) return launch_variant<2, true, 2, 8>(p, sms, st);
   if (nz == 1) FMCW_WF(1);
   if (nz == 2) FMCW_WF(2);
   FMCW_WF(4);

@@ -238,12 +238,12 @@ __global__ void __launch_bounds__(256) stft_coef_kernel(StftTables t, StftGeom g
   const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int p = gw; p < nb; p += nw) {
     const long long bin = t.bins[p];
-    double acc = (odd && lane == 0) ? (double)t.win[half] : 0.0;
+    double acc = (odd && lane == 0) ? t.win_d[half] : 0.0;
     for (int m = lane; m < half; m += 32) {
       const long long twod = odd ? (2 * m + 2) : (2 * m + 1);
       const long long r = (twod * bin) % mod;
       const int lo = half - 1 - m, hi = odd ? (half + 1 + m) : (half + m);
-      acc += ((double)t.win[lo] + (double)t.win[hi]) * cospi((double)r / (double)nfft);
+      acc += (t.win_d[lo] + t.win_d[hi]) * cospi((double)r / (double)nfft);
     }
 #pragma unroll
     for (int k = 16; k >= 1; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
@@ -966,10 +966,145 @@ static cudaError_t launch_main_variant(const StftTables& t, const StftGeom& g, c
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Float64 STFT (FMCW_OPT_STFT_PRECISION = 1): the reference arithmetic (RP:276-299 in double) for callers that need the
+// 1e-4 relative tolerance on bins far below the -140 dB the TF32 x 2 tensor-core kernel guarantees.  Any window, any hop.
+// A CTA owns NC columns; the folded, windowed taps of its columns sit in shared memory as float64; the cos / sin of a
+// tile of 8 bins are evaluated once per CTA by sincospi of the exactly reduced argument; a thread owns a column and walks
+// the sorted distinct bins, running the interp1 as the bins complete (same bookkeeping as the generic-window kernels).
+// ------------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(128) stft_precise_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x,
+                                                           float* __restrict__ out, unsigned long long capacity_cols,
+                                                           unsigned long long ld_cols, int* d_err, int NC) {
+  const StftPlan* P = t.plan;
+  if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
+  constexpr int QF = 16, BT = 8;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int win = (int)g.win, half = win / 2, odd = win & 1;
+  double* s_eo = reinterpret_cast<double*>(s_raw);              // [2*half + 1][NC]: even parts, odd parts, centre tap
+  double* s_cf = s_eo + (size_t)(2 * half + 1) * NC;            // [half][2*BT] cos of 8 bins | sin of 8 bins
+  float* s_stage = reinterpret_cast<float*>(s_cf + (size_t)half * 2 * BT);   // [warps][32][QF+1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
+  const unsigned long long ncl = ce - cb;
+  if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
+  const int nq = P->nq, nb = P->nb;
+  const unsigned long long nfft = P->nfft;
+  const long long mod = (long long)(2 * nfft);
+  const double inv = 1.0 / sqrt(P->pmax_raw);
+  const unsigned long long n_blk = (ncl + NC - 1) / NC;
+  const uint32_t a_stage = smem_u32(s_stage) + (uint32_t)(warp * 32 * (QF + 1) * 4);
+  const uint32_t a_st_lane = a_stage + (uint32_t)(lane * (QF + 1) * 4);
+  const bool owner = tid < NC;
+  for (unsigned long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+    unsigned long long col = cb + blk * NC + tid;
+    const bool act = owner && col < ce;
+    if (!(col < ce)) col = ce - 1;
+    __syncthreads();                                     // the previous block's taps are consumed
+    if (owner) {
+      const sig_t* xs = x + (col * g.hop - off);
+      for (int m = 0; m < half; ++m) {
+        const int lo = half - 1 - m, hi = odd ? (half + 1 + m) : (half + m);
+        const double ylo = t.win_d[lo] * inv * xs[lo], yhi = t.win_d[hi] * inv * xs[hi];
+        s_eo[(size_t)m * NC + tid] = ylo + yhi;
+        s_eo[(size_t)(half + m) * NC + tid] = ylo - yhi;
+      }
+      s_eo[(size_t)(2 * half) * NC + tid] = odd ? t.win_d[half] * inv * xs[half] : 0.0;
+    }
+    const unsigned long long warp_col0 = cb + blk * NC + (unsigned long long)warp * 32;
+    const int ncols_valid = (warp * 32 >= NC || warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 32ull ? (ce - warp_col0) : 32ull);
+    float* out_warp = out + (warp_col0 - cb) * (unsigned long long)nq;
+    float prev = 0.f;
+    int qcur = 0;
+    for (int pb = 0; pb < nb; pb += BT) {
+      __syncthreads();                                   // previous coefficient tile consumed (and the taps written)
+      for (int i = tid; i < half * BT; i += blockDim.x) {
+        const int m = i / BT, j = i - m * BT, p = pb + j;
+        double sv = 0.0, cv = 0.0;
+        if (p < nb) {
+          // phase (m + d) * w with d = 1/2 (even windows) or 1 (odd windows, centre tap apart): 2*pi*(2m + 2d)*bin / (2 nfft)
+          const long long r = ((long long)(2 * m + (odd ? 2 : 1)) * (long long)t.bins[p]) % mod;
+          sincospi((double)r / (double)nfft, &sv, &cv);
+        }
+        s_cf[(size_t)m * 2 * BT + j] = cv;
+        s_cf[(size_t)m * 2 * BT + BT + j] = sv;
+      }
+      __syncthreads();
+      if (warp * 32 < NC) {
+        double re[BT], im[BT];
+        const double yc = s_eo[(size_t)(2 * half) * NC + (owner ? tid : 0)];
+#pragma unroll
+        for (int j = 0; j < BT; ++j) { re[j] = yc; im[j] = 0.0; }
+        for (int m = 0; m < half; ++m) {
+          const double e = s_eo[(size_t)m * NC + tid], o = s_eo[(size_t)(half + m) * NC + tid];
+          const double* cf = s_cf + (size_t)m * 2 * BT;
+#pragma unroll
+          for (int j = 0; j < BT; ++j) { re[j] = fma(e, cf[j], re[j]); im[j] = fma(o, cf[BT + j], im[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < BT; ++j) {
+          const int p = pb + j;
+          if (p < nb) {
+            const float pw = (float)fma(re[j], re[j], im[j] * im[j]);
+            const float db = fmaf(K_DB, lg2_approx(pw), __ldg(t.kcb + p));
+            if (p > 0) {
+              const int qe = __ldg(t.qend + p);
+              for (; qcur < qe; ++qcur) {
+                const float v = fmaf(__ldg(t.aq + qcur), db - prev, prev);
+                if (LAYOUT == 0) {
+                  const int slot = qcur & (QF - 1);
+                  sts32(a_st_lane + (uint32_t)(slot * 4), v);
+                  if (slot == QF - 1) flush_stage<QF, 32>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - (QF - 1), QF, lane);
+                } else if (act) {
+                  out[(unsigned long long)qcur * ld_cols + (col - cb)] = v;
+                }
+              }
+            }
+            prev = db;
+          }
+        }
+      }
+    }
+    if (LAYOUT == 0 && warp * 32 < NC) {
+      const int rem = qcur & (QF - 1);
+      if (rem) flush_stage<QF, 32>(a_stage, ncols_valid, out_warp, (unsigned long long)nq, qcur - rem, rem, lane);
+    }
+  }
+}
+
+static cudaError_t launch_stft_precise(const StftTables& t, const StftGeom& g, const sig_t* x, float* out,
+                                       unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
+                                       cudaStream_t st, int sms) {
+  const int half = (int)g.win / 2;
+  const int NC = g.win <= 96 ? 128 : g.win <= 192 ? 64 : 32;
+  const size_t smem = ((size_t)(2 * half + 1) * NC + (size_t)half * 16) * sizeof(double) + (size_t)4 * 32 * 17 * sizeof(float);
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  cudaError_t e;
+  if (layout == 0) {
+    e = cudaFuncSetAttribute(stft_precise_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    stft_precise_kernel<0><<<sms * per_sm, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err, NC);
+  } else {
+    e = cudaFuncSetAttribute(stft_precise_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    stft_precise_kernel<1><<<sms * per_sm, 128, smem, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err, NC);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout, int* d_err,
-                             cudaStream_t st, const double* gmax_dev) {
+                             cudaStream_t st, const double* gmax_dev, int precise) {
   const int sms = sm_count();
+  if (precise) {
+    if (gmax_dev) {
+      cudaError_t e0 = launch_stft_set_max_dev(t, gmax_dev, st);
+      if (e0 != cudaSuccess) return e0;
+    }
+    return launch_stft_precise(t, g, x, out, capacity_cols, ld_cols, layout, d_err, st, sms);
+  }
   if (g.win == 20 && stft_variant() < 0)
     return launch_stft_tc_main(t, g, x, out, t.tcB, capacity_cols, ld_cols, layout, d_err, st, gmax_dev);
   if (gmax_dev) {

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
         // window DC response at this bin: sum_m (w[9-m] + w[10+m]) cos((m+1/2) w)
         for (int m = 0; m < TC_HALF; ++m) {
           const long long r = ((long long)(2 * m + 1) * bin) % mod;
-          cv += ((double)t.win[TC_HALF - 1 - m] + (double)t.win[TC_HALF + m]) * cospi((double)r / (double)nfft);
+          cv += (t.win_d[TC_HALF - 1 - m] + t.win_d[TC_HALF + m]) * cospi((double)r / (double)nfft);
         }
       }
       cv *= sc;

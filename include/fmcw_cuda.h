@@ -139,8 +139,18 @@ FMCW_API fmcw_status fmcw_synchronize(fmcw_handle* h);
 /* Options.  FMCW_OPT_ASYNC_HOST = 1: fmcw_process_frames / fmcw_run with (pinned) host buffers return as soon as the
  * copies and kernels are queued, so that two handles can overlap one recording's D2H with the next one's H2D; the
  * intensity copy then covers the upper bound of the column count and the results are valid after fmcw_synchronize
- * (sizes from fmcw_get_info). */
-enum { FMCW_OPT_ASYNC_HOST = 1 };
+ * (sizes from fmcw_get_info).
+ *
+ * FMCW_OPT_STFT_PRECISION = 2: arithmetic of the STFT main kernel (RP:276-299).
+ *   0 (default): tcgen05 tensor cores, operands split hi + lo in TF32 (2^-22 of the mean-removed column), float64 column
+ *      mean through a float64-tabulated window response.  Against the double-precision reference: 1e-3 dB for bins above
+ *      -60 dB and 1e-4 relative (of P/max) down to -140 dB on every scene; below that the split is the floor (measured
+ *      4e-4 in (-180,-140] dB, 2e-3 in (-220,-180] dB on a scene whose columns carry strong 0-200 Hz content; 5e-5 down to
+ *      -260 dB when the slow-time signal is a level plus noise).
+ *   1: float64 CUDA-core kernel, any window: 1e-4 relative at every finite level (measured 5e-6); about 13x the time of
+ *      the default kernel (3.4 ms instead of 0.27 ms per 5,000-frame recording on a B200).
+ * tests/helpers.py::assert_spectrogram_contract asserts exactly these bounds. */
+enum { FMCW_OPT_ASYNC_HOST = 1, FMCW_OPT_STFT_PRECISION = 2 };
 FMCW_API fmcw_status fmcw_set_option(fmcw_handle* h, int option, int64_t value);
 FMCW_API fmcw_status fmcw_get_info(fmcw_handle* h, fmcw_run_info* info);   /* synchronises */
 

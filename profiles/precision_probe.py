@@ -43,17 +43,34 @@ for (NTS, PN, nf) in [(128, 64, 60), (64, 16, 80), (256, 256, 6)]:
     print(" synth mismatches", int((g != case["iq"]).sum()))
     h.close()
 
-# spectrogram error by level band (end to end)
-case = H.make_case(n_frames=60, NTS=128, PN=64)
-ref = H.oracle_no(case)
-h = FmcwCuda(case["cfg"], case["calib"])
-out, inten = h.run(case["iq"])
-nc = h.info()["ncol_local"]
-g = inten[:nc].T.astype(np.float64); r = ref["stft"]["intensity"]
-fin = np.isfinite(r) & np.isfinite(g)
-for lo, hi in [(-60, 1), (-100, -60), (-140, -100), (-180, -140), (-220, -180), (-260, -220), (-400, -260)]:
-    m = fin & (r > lo) & (r <= hi)
-    if m.any():
-        rel = np.abs(10 ** ((g[m] - r[m]) / 20) - 1)
-        print(f" band ({lo:4d},{hi:4d}] dB: n={m.sum():8d}  max |ddB|={np.abs(g[m]-r[m]).max():.2e}  max rel={rel.max():.2e}  p99.9 rel={np.quantile(rel,0.999):.2e}")
-h.close()
+# spectrogram error by level band (end to end), default (tensor-core TF32 x 2) and FMCW_OPT_STFT_PRECISION = 1 (float64)
+from fmcw_radar_processing_b200 import _lib as L
+BANDS = [(-60, 1), (-100, -60), (-140, -100), (-180, -140), (-220, -180), (-260, -220), (-400, -260)]
+for scene_name, scene in (("C1 scene (single target)", None), ("C2 scene (torso + limbs)", synth.scene_c2(2))):
+    case = H.make_case(n_frames=60, NTS=128, PN=64, scene=scene)
+    ref = H.oracle_no(case)
+    r = ref["stft"]["intensity"]
+    for mode in (0, 1):
+        h = FmcwCuda(case["cfg"], case["calib"])
+        h.set_option(L.OPT_STFT_PRECISION, mode)
+        out, inten = h.run(case["iq"])
+        nc = h.info()["ncol_local"]
+        g = inten[:nc].T.astype(np.float64)
+        print(f"{scene_name}, STFT precision mode {mode}: non-finite agree {np.array_equal(np.isfinite(g), np.isfinite(r))}")
+        fin = np.isfinite(r) & np.isfinite(g)
+        for lo, hi in BANDS:
+            m = fin & (r > lo) & (r <= hi)
+            if m.any():
+                rel = np.abs(10 ** ((g[m] - r[m]) / 20) - 1)
+                print(f" band ({lo:4d},{hi:4d}] dB: n={m.sum():8d}  max |ddB|={np.abs(g[m]-r[m]).max():.2e}  max rel={rel.max():.2e}  p99.9 rel={np.quantile(rel,0.999):.2e}")
+        h.close()
+
+# cost of the float64 kernel on the C2 workload (5,000 frames)
+import torch
+from bench import DeviceRun, time_device
+for mode in (0, 1):
+    rr = DeviceRun("c2", 5000, 0, 1, 0)
+    rr.h.set_option(L.OPT_STFT_PRECISION, mode)
+    ms, st = time_device(rr, lambda: rr.h.run(rr.iq, rr.out, rr.inten), 10, 3, lambda: torch.cuda.synchronize())
+    print(f"C2 5,000 frames, STFT precision mode {mode}: step {ms:.4f} ms, stft_main {st[3]:.4f} ms")
+    rr.close()
