@@ -16,7 +16,7 @@ def _txt(node) -> float:
 
 
 def fmcw_configurations(sXML, window_length: int = 20, overlap: int | None = None, range_fft_size: int = 256,
-                        Doppler_fft_size: int = 16, rx_select: int = 1, peak_mode: str = "strongest",
+                        Doppler_fft_size: int = 16, rx_select: int = 1, peak_mode: str = "first",
                         kaiser_beta: float = 3.0, MAX_FREQ_BINS: int = 1024, adc_scale: float = 4095.0,
                         batch_size: int = 100) -> "OrderedDict[str, float]":
     """RP:89-154, 178-179.  ``sXML`` is the xml2struct-shaped dict the parser returns.  ``rx_select`` is

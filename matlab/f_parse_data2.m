@@ -1,15 +1,9 @@
 function [frame, frame_count, calib_data, sXML] = f_parse_data2(fdata)
 % Shim of the vendor parser the reference calls at radar_processing.m line 86 but does not ship.
-% Reads the FMCWRAW1 container defined in fmcw_radar_processing_b200/parse.py.  For the GPU path `frame`
-% is the raw int16 block [2 x NTS x PN x RX x N]; frame_structs() below converts it to the
-% frame(k).Chirp [NTS x PN x RX] complex doubles the untouched reference loop expects.
-    sXML = xml2struct([fdata '.xml']);
-    fid = fopen([fdata '.raw.bin'], 'r', 'ieee-le');
-    magic = fread(fid, 8, 'uint8=>char')';
-    assert(strcmp(magic, 'FMCWRAW1'));
-    hdr = fread(fid, 5, 'uint32');            % n_frames, n_rx, PN, NTS, n_cal
-    frame_count = hdr(1);
-    calib_data = fread(fid, 2*hdr(2)*hdr(5), 'double')' / 4095;
-    frame = reshape(fread(fid, inf, 'int16=>int16'), [2, hdr(4), hdr(3), hdr(2), hdr(1)]);
-    fclose(fid);
+% Reads the FMCWRAW1 container defined in fmcw_radar_processing_b200/parse.py and returns what the UNTOUCHED
+% reference loop expects: frame(k).Chirp = [NTS x PN x RX] complex double, ADC codes / 4095 (lines 199-202),
+% calib_data = row vector [I_rx1 Q_rx1 I_rx2 Q_rx2 ...] / 4095 (lines 167-172), sXML with .Text leaves (line 94).
+% f_parse_data2_raw.m is the variant the GPU path uses (frames stay int16).
+    [raw, frame_count, calib_data, sXML] = f_parse_data2_raw(fdata);
+    frame = frame_structs(raw);
 end

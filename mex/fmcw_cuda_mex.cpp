@@ -7,7 +7,7 @@
 //
 // iq    int16 [2 x NTS x PN x RX x N]  (MATLAB column-major == C [frame][rx][chirp][sample][I,Q])
 // cfg   struct with the fmcw_configurations field names (RP:645-672) plus kaiser_beta, MAX_FREQ_BINS,
-//       adc_scale, rx_select (1-based), peak_mode (0 strongest / 1 first)
+//       adc_scale, rx_select (1-based), peak_mode (0 strongest / 1 first = default, the vendor picker's order)
 // out   struct: detected, range_idx (1-based), range_mag, doppler_idx (1-based), range_max_abs [256 x N],
 //       doppler_row [ND x N] complex, slow_time_mag [PN x N], T [1 x ncol], frequency [1 x 1024],
 //       intensity [1024 x ncol] single, nfft, pmax
@@ -53,7 +53,7 @@ bool read_config(const mxArray* s, fmcw_config& c, std::string& missing) {
   U(num_chirps_per_frame, true, 0); U(range_fft_size, true, 256); U(Doppler_fft_size, true, 16);
   U(max_num_targets, true, 1); U(window_length, true, 20); U(overlap, true, 19); U(MAX_FREQ_BINS, false, 1024);
   c.rx_select = (uint32_t)field(s, "rx_select", 1, false, missing) - 1;   // MATLAB 1-based
-  U(peak_mode, false, 0);
+  U(peak_mode, false, 1);
   D(frame_time, false, 0.15); D(PRT, true, 0); D(Bandwidth, false, 0); D(carrier_frequency, false, 0);
   D(sampling_frequency, false, 0); D(IF_scale, true, 0); D(range_threshold, true, 200); D(Doppler_threshold, true, 50);
   D(min_distance, true, 0.9); D(max_distance, true, 25.0); c.lambda = field(s, "lambda", 0, false, missing);

@@ -46,7 +46,7 @@ void fill_config(napi_env env, napi_value o, fmcw_config& c) {
 #define D(n, d) c.n = num(env, o, #n, d)
   U(num_Tx_antennas, 1); U(num_Rx_antennas, 1); U(num_ADC_samples_per_chirp, 0); U(num_chirps_per_frame, 0);
   U(range_fft_size, 256); U(Doppler_fft_size, 16); U(max_num_targets, 1); U(window_length, 20); U(overlap, 19);
-  U(MAX_FREQ_BINS, 1024); U(peak_mode, 0);
+  U(MAX_FREQ_BINS, 1024); U(peak_mode, 1);
   c.rx_select = (uint32_t)num(env, o, "rx_select", 1) - 1;
   D(frame_time, 0.15); D(PRT, 0); D(Bandwidth, 0); D(carrier_frequency, 0); D(sampling_frequency, 0); D(IF_scale, 0);
   D(range_threshold, 200); D(Doppler_threshold, 50); D(min_distance, 0.9); D(max_distance, 25.0);

@@ -80,15 +80,19 @@ def f_parse_data2(iq_codes, calib_codes, sxml, adc_scale=4095.0):
 
 
 def f_search_peak(sig, length, threshold, max_num, min_distance, max_distance, dist_per_bin,
-                  peak_mode="strongest"):
+                  peak_mode="first"):
     """Shim of the unshipped range peak picker called at RP:211 / RP:469.
 
     5-point local maximum: ``s[n] >= s[n-1], s[n-2]`` and ``s[n] > s[n+1], s[n+2]`` for
     n = 3..length-2 (1-based), ``s[n] >= threshold`` and ``(n-1)*dist_per_bin`` inside
-    ``[min_distance, max_distance]``.  ``peak_mode='strongest'`` keeps the ``max_num``
-    largest candidates (ties: lowest index first), matching RP:258's "strongest target";
-    ``'first'`` keeps the first ``max_num`` in increasing range.  Returns 1-based indices
-    and magnitudes (row vectors, empty when none).
+    ``[min_distance, max_distance]``.  ``peak_mode='first'`` (default) keeps the first ``max_num``
+    candidates in increasing range: the vendor SDK demo this function comes from walks n upward and
+    stops appending once ``max_num`` peaks are found, so with ``max_num_targets = 1`` (RP:129) the
+    NEAREST peak above the threshold is tracked.  ``'strongest'`` keeps the ``max_num`` largest
+    candidates (ties: lowest index first), what RP:258's comment "Index of strongest target" reads
+    like.  The two differ only when a frame holds several peaks above ``range_threshold`` inside
+    the distance gate (tests/test_gpu_parity.py::test_two_targets_peak_modes).  Returns 1-based
+    indices and magnitudes (row vectors, empty when none).
     """
     s = np.asarray(sig, dtype=np.float64).reshape(-1)
     cand = []
@@ -149,14 +153,14 @@ class Config:
     MAX_FREQ_BINS: int = 1024         # RP:293
     batch_size: int = 100             # RP:189
     max_plots: int = 4                # RP:443
-    peak_mode: str = "strongest"      # shim choice, see f_search_peak
+    peak_mode: str = "first"          # shim choice, see f_search_peak
     range_window_func: np.ndarray = field(default=None, repr=False)
     doppler_window_func: np.ndarray = field(default=None, repr=False)
     array_bin_range: np.ndarray = field(default=None, repr=False)
 
 
 def configure(sxml, window_length=20, overlap=None, range_fft_size=256, Doppler_fft_size=16,
-              peak_mode="strongest") -> Config:
+              peak_mode="first") -> Config:
     """RP:89-154 and RP:178-179, line by line."""
     frame_time = 150 * 1e-3                                                    # RP:91
     up = _txt(sxml["Device"]["BaseEndpoint"]["chirpDuration_ns"]) * 1e-9      # RP:94
@@ -311,6 +315,41 @@ def stft_literal(iq_abs, cfg: Config):
     a = (fq - Fo[j]) / (Fo[j + 1] - Fo[j])
     out = Po[j, :] + a[:, None] * (Po[j + 1, :] - Po[j, :])
     return dict(T=T, frequency=fq, intensity=out, nfft=nfft, pmax=G, P=P)
+
+
+def stft_literal_chunked(iq_abs, cfg: Config, col_chunk=2048):
+    """The same operations as ``stft_literal`` (full-nfft one-sided PSD, fftshift, max(max(P)), 20*log10, interp1 over
+    the sorted fine grid), applied to blocks of columns so that C1's 16,385 x 31,981 matrix P (4.2 GB, RP:276) never has
+    to be resident: pass 1 finds max(max(P)) (RP:282), pass 2 normalises and resamples each block (RP:283-299).  Columns
+    are independent in every step but the maximum, so the results are bit-identical to ``stft_literal``
+    (tests/test_oracle_stft.py)."""
+    x = np.asarray(iq_abs, dtype=np.float64).reshape(-1)
+    win = cfg.window_length
+    w = _win.kaiser(win, cfg.kaiser_beta, sym=True)
+    nfft, fs, hop, ncol, T, fq = stft_axes(len(x), cfg)
+    segs = np.lib.stride_tricks.sliding_window_view(x, win)[::hop][:ncol]
+    F = np.arange(nfft // 2 + 1) * fs / nfft
+    Fs_ = sfft.fftshift(F)
+    order = np.argsort(Fs_, kind="stable")
+    Fo = Fs_[order]
+    j = np.clip(np.searchsorted(Fo, fq, side="right") - 1, 0, len(Fo) - 2)
+    a = (fq - Fo[j]) / (Fo[j + 1] - Fo[j])
+
+    def block(c0):
+        seg = segs[c0:c0 + col_chunk] * w[None, :]
+        S = sfft.fft(seg, nfft, axis=1)[:, :nfft // 2 + 1].T
+        P = (np.abs(S) ** 2) / (fs * np.sum(w ** 2))
+        P[1:nfft // 2, :] *= 2
+        return sfft.fftshift(P, axes=0)
+
+    G = max(float(block(c0).max()) for c0 in range(0, ncol, col_chunk))
+    out = np.empty((len(fq), ncol))
+    for c0 in range(0, ncol, col_chunk):
+        with np.errstate(divide="ignore"):
+            psd = 20 * np.log10(np.abs(block(c0)) / G)
+        Po = psd[order, :]
+        out[:, c0:c0 + col_chunk] = Po[j, :] + a[:, None] * (Po[j + 1, :] - Po[j, :])
+    return dict(T=T, frequency=fq, intensity=out, nfft=nfft, pmax=G)
 
 
 def _dtft_bins(fq, nfft, fs):

@@ -9,7 +9,7 @@ from oracle import fmcw_oracle as O
 
 
 def make_case(n_frames=40, NTS=128, PN=64, n_rx=1, scene=None, seed=1, frame0=0, window_length=20, overlap=None,
-              rx_select=1, peak_mode="strongest", sigma=2.0):
+              rx_select=1, peak_mode="first", sigma=2.0):
     sx = O.make_sxml(numSamplesPerChirp=NTS, numChirpsPerFrame=PN, numAntennasRx=n_rx)
     ocfg = O.configure(sx, window_length=window_length, overlap=overlap, peak_mode=peak_mode)
     cfg = fmcw_configurations(sx, window_length=window_length, overlap=overlap, rx_select=rx_select, peak_mode=peak_mode)

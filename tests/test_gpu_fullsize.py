@@ -131,3 +131,30 @@ def test_c3_streaming_200k_frames():
         assert np.abs(got[strong] - ref["intensity"][strong]).max() < 1e-3
     assert bool(torch.isfinite(inten[::4096]).all())
     h.close()
+
+
+def test_c1_full_size_against_the_literal_oracle():
+    """BASELINE.json configs[0] at its stated size: seed 1, 1 RX, 64 chirps x 128 samples, 500 frames, single moving point
+    target.  The frame chain against the serial oracle (RP:197-261) on every frame, and the spectrogram against the LITERAL
+    form of RP:270-299 (nfft = 32,768; P = 16,385 x 31,981 doubles, walked in blocks of columns), not the restated one."""
+    import time
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    from tests import helpers as H
+    case = H.make_case(n_frames=500, NTS=128, PN=64, seed=1)
+    t0 = time.time()
+    ref = H.oracle_no(case, stft=None)
+    h = FmcwCuda(case["cfg"], case["calib"])
+    out, inten = h.run(case["iq"])
+    info = h.info()
+    d = ref["detected"]
+    assert d.all() and np.array_equal(out["detected"].astype(bool), d)
+    assert np.array_equal(out["range_bin"], ref["range_idx"] - 1) and np.array_equal(out["doppler_bin"], ref["doppler_idx"] - 1)
+    e_db, e_rel = H.db_errors(out["range_max_abs"], ref["range_tx1rx1_max_abs"].T)
+    assert e_db < 1e-3 and e_rel < 2e-4
+    assert info["L_total"] == 32000 and info["nfft"] == 32768 and info["ncol_local"] == 31981
+    x = np.abs(ref["slow_time_signal_all_frames"])
+    lit = O.stft_literal_chunked(x, case["ocfg"], col_chunk=1024)
+    assert lit["intensity"].shape == (1024, 31981)
+    H.assert_spectrogram_contract(inten[:31981].T, lit["intensity"])
+    assert info["pmax_raw"] * 0 == 0 and time.time() - t0 < 600
+    h.close()

@@ -98,12 +98,14 @@ def test_search_peak_shim():
     s = np.zeros(256)
     s[[10, 30, 31, 50, 200]] = [300, 500, 500, 900, 5000]
     d = 0.375
-    idx, mag = O.f_search_peak(s, 256, 200, 1, 0.9, 25.0, d)
+    idx, mag = O.f_search_peak(s, 256, 200, 1, 0.9, 25.0, d, peak_mode="strongest")
     assert list(idx) == [51] and list(mag) == [900]                 # strongest inside the gate (bin 200 is > 25 m)
-    idx, _ = O.f_search_peak(s, 256, 200, 1, 0.9, 25.0, d, peak_mode="first")
-    assert list(idx) == [11]
-    idx, _ = O.f_search_peak(s, 256, 200, 3, 0.9, 25.0, d)
+    idx, mag = O.f_search_peak(s, 256, 200, 1, 0.9, 25.0, d)        # default: the vendor order, nearest peak first
+    assert list(idx) == [11] and list(mag) == [300]
+    idx, _ = O.f_search_peak(s, 256, 200, 3, 0.9, 25.0, d, peak_mode="strongest")
     assert list(idx) == [51, 32, 11]                                # plateau 30/31: >= left, > right -> index 32 (1-based)
+    idx, _ = O.f_search_peak(s, 256, 200, 3, 0.9, 25.0, d)
+    assert list(idx) == [11, 32, 51]
     idx, _ = O.f_search_peak(s, 256, 1000, 1, 0.9, 25.0, d)
     assert idx.size == 0
     s2 = np.zeros(256); s2[2] = 900                                 # 0.75 m < min_distance

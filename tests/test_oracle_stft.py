@@ -78,3 +78,14 @@ def test_column_range_restriction():
     full = O.stft_restated(x, cfg)
     part = O.stft_restated(x, cfg, pmax_raw=full["pmax_raw"], col_range=(100, 900))
     assert np.array_equal(part["intensity"], full["intensity"][:, 100:900])
+
+
+def test_literal_in_column_blocks_is_bit_identical():
+    """The C1-size literal check of the GPU suite walks P in blocks of columns; same bits as the one-shot literal form."""
+    sx = O.make_sxml(numSamplesPerChirp=64, numChirpsPerFrame=16)
+    cfg = O.configure(sx)
+    rng = np.random.default_rng(5)
+    x = np.abs(2400 + 30 * rng.standard_normal(700) + 200 * np.sin(np.arange(700) * 0.05))
+    a = O.stft_literal(x, cfg)
+    b = O.stft_literal_chunked(x, cfg, col_chunk=97)
+    assert np.array_equal(a["intensity"], b["intensity"]) and a["pmax"] == b["pmax"]
