@@ -279,6 +279,20 @@ class FmcwCuda:
         return intensity
 
     # ---- extras ----
+    def stft_finegrid(self, f_lo: float = 0.0, f_hi: float = 150.0, max_rows: int = 2048, out=None):
+        """psd band of the last STFT on the fine grid (RP:283, the matrix surf draws at RP:333 between ylim [0 150]).
+        Returns (psd [ncol][n_rows] float32, F [n_rows] float64 Hz)."""
+        info = self.info()
+        ncl = info["ncol_local"]
+        if out is None:
+            out = np.empty((max(1, ncl), max_rows), dtype=np.float32)
+        fb, st, nr, nc = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.fmcw_stft_finegrid(self._h, f_lo, f_hi, max_rows, _ptr(out), out.shape[0], C.byref(fb), C.byref(st),
+                                                C.byref(nr), C.byref(nc)))
+        F = (fb.value + np.arange(nr.value) * st.value) * (1.0 / self.cfg["PRT"]) / info["nfft"]
+        flat = out.reshape(-1)[:nc.value * nr.value] if isinstance(out, np.ndarray) else out.view(-1)[:nc.value * nr.value]
+        return flat.reshape(nc.value, nr.value), F
+
     def range_spectrum(self, iq, frame: int, chirp: int) -> np.ndarray:
         """abs(range_fft(:, chirp)) of one frame (RP:410-411), 0-based indices."""
         out = np.empty(self.NR, dtype=np.float32)

@@ -226,6 +226,8 @@ void fill_tables(fmcw_handle* h) {
 
 fmcw_status read_info(fmcw_handle* h) {
   CK(cudaStreamSynchronize(h->stream), "synchronize");
+  // a look-ahead plan forked by the last call may still be rewriting the plan struct on the side stream
+  if (h->lookahead) CK(cudaStreamSynchronize(h->side), "synchronize look-ahead plan");
   unsigned long long nd = 0;
   if (h->frames_done) CK(cudaMemcpy(&nd, h->ndet.p, sizeof(nd), cudaMemcpyDeviceToHost), "read n_det");
   h->n_det_host = nd;
@@ -374,8 +376,7 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
   if (!h->planned) {
     int spec_mode = 0;
     CK(join_lookahead(h, spec_mode), "join look-ahead plan");
-    static int use_graph = -1;
-    if (use_graph < 0) { const char* v = getenv("FMCW_GRAPH"); use_graph = (v && atoi(v) == 0) ? 0 : 1; }
+    static const int use_graph = env_int("FMCW_GRAPH", 1) != 0;
     const bool graphable = use_graph && from_device_count && compute_max && spec_mode == 2 && ++h->mx_eligible_calls > 1;
     if (graphable) {
       if (!h->mx_exec || memcmp(&h->mx_key_tables, &h->st, sizeof(StftTables)) != 0 || h->mx_key_xc != h->xc.p) {
@@ -993,6 +994,44 @@ fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, uint64_t co
       frequency[q] = std::pow(10.0, y);
     }
   }
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_stft_finegrid(fmcw_handle* h, double f_lo_hz, double f_hi_hz, uint32_t max_rows, float* psd,
+                               uint64_t capacity_cols, uint64_t* first_bin, uint64_t* bin_step, uint64_t* n_rows, uint64_t* ncol) {
+  if (!h || !psd) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  if (!h->planned) return fail(h, FMCW_ERR_STATE, "no STFT has run on this handle");
+  if (!(f_hi_hz >= f_lo_hz) || f_lo_hz < 0.0 || max_rows == 0) return fail(h, FMCW_ERR_CONFIG, "bad band or max_rows");
+  if (h->cfg.window_length > 170) return fail(h, FMCW_ERR_CONFIG, "fmcw_stft_finegrid supports window_length <= 170");
+  if (!h->have_info) { fmcw_status s = read_info(h); if (s != FMCW_OK) return s; }
+  const StftPlan& P = h->plan_host;
+  if (P.valid <= 0) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length slow-time samples");
+  const double df = h->geom.fs / (double)P.nfft;
+  unsigned long long j0 = (unsigned long long)std::ceil(f_lo_hz / df - 1e-9), j1 = (unsigned long long)std::floor(f_hi_hz / df + 1e-9);
+  if (j1 > P.nfft / 2) j1 = P.nfft / 2;
+  if (j0 > j1) return fail(h, FMCW_ERR_CONFIG, "no fine-grid bin inside the band");
+  const unsigned long long span = j1 - j0 + 1;
+  const unsigned long long step = (span + max_rows - 1) / max_rows;
+  const unsigned long long rows = (span + step - 1) / step;
+  const unsigned long long ncl = P.col_end - P.col_begin;
+  if (ncl > capacity_cols) return fail(h, FMCW_ERR_SIZE, "capacity_cols is smaller than the column count");
+  const bool dev_out = is_device_ptr(psd);
+  float* d_out = psd;
+  if (!dev_out) {
+    CK(h->inten.ensure((size_t)ncl * rows * 4), "alloc psd staging");
+    d_out = h->inten.as<float>();
+  }
+  CK(launch_stft_finegrid(h->st, h->geom, h->xc.as<sig_t>(), d_out, j0, step, (unsigned)rows, ncl, h->derr.as<int>(), h->stream),
+     "stft finegrid kernel");
+  if (!dev_out) CK(cudaMemcpyAsync(psd, d_out, (size_t)ncl * rows * 4, cudaMemcpyDeviceToHost, h->stream), "D2H psd");
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  if (first_bin) *first_bin = j0;
+  if (bin_step) *bin_step = step;
+  if (n_rows) *n_rows = rows;
+  if (ncol) *ncol = ncl;
   return FMCW_OK;
 }
 

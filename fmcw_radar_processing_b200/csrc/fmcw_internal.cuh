@@ -44,6 +44,9 @@ struct ChainParams {
 
 size_t chain_smem_bytes(uint32_t PN);
 cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st);
+// Process-wide settings, read once (C++11 thread-safe static initialisation): handles may be used from any thread.
+int device_sm_count();                      // SMs of the current device (148 on B200)
+int env_int(const char* name, int dflt);    // atoi(getenv(name)) or dflt
 // one warp per frame, two chirps per lane (frame_chain_warp.cu); launch_frame_chain dispatches to it when supported
 bool chain_warp_supported(const ChainParams& p);
 cudaError_t launch_frame_chain_warp(const ChainParams& p, cudaStream_t st);
@@ -111,6 +114,10 @@ cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream
 cudaError_t launch_stft_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int layout,
                              int* d_err, cudaStream_t st, const double* gmax_dev = nullptr, int precise = 0);
+
+cudaError_t launch_stft_finegrid(const StftTables& t, const StftGeom& g, const sig_t* x, float* psd, unsigned long long first_bin,
+                                 unsigned long long bin_step, unsigned n_rows, unsigned long long capacity_cols, int* d_err,
+                                 cudaStream_t st);
 
 // tensor-core (tcgen05) STFT main kernel, window_length = 20 (stft_tc.cu)
 size_t stft_tc_table_bytes(int nb_max);

@@ -89,6 +89,15 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+int device_sm_count() {
+  static const int sms = [] { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 148; }();
+  return sms;
+}
+
 static size_t chain_smem_bytes_nw(uint32_t PN, int nw) {
   size_t b = (size_t)nw * 2 * XCH_CHIRP * sizeof(float2);             // transpose slices (4,352 B per warp)
   b += 256 * sizeof(float2);                                          // tw_pair
@@ -412,14 +421,11 @@ static cudaError_t launch_chain_variant(const ChainParams& p, int sms, cudaStrea
 
 cudaError_t launch_frame_chain(const ChainParams& p, cudaStream_t st) {
   if (p.n_frames == 0) return cudaSuccess;
-  static int variant = -1;   // FMCW_CHAIN_VARIANT=0: the one-CTA-per-frame kernel below (kept for A/B runs and odd shapes)
-  if (variant < 0) { const char* v = getenv("FMCW_CHAIN_VARIANT"); variant = (v && atoi(v) == 0) ? 0 : 1; }
+  // FMCW_CHAIN_VARIANT=0: the one-CTA-per-frame kernel below (kept for A/B runs and odd shapes)
+  static const int variant = env_int("FMCW_CHAIN_VARIANT", 1) == 0 ? 0 : 1;
   if (variant == 1 && chain_warp_supported(p)) return launch_frame_chain_warp(p, st);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static int nt = 0;
-  if (!nt) { const char* v = getenv("FMCW_CHAIN_THREADS"); const int r = v ? atoi(v) : 0; nt = (r == 256) ? 256 : 128; }   // 128 measured fastest (64 / 96 / 128 / 256: 0.192 / 0.186 / 0.185 / 0.199 ms on C2)
+  const int sms = device_sm_count();
+  static const int nt = env_int("FMCW_CHAIN_THREADS", 128) == 256 ? 256 : 128;   // 128 measured fastest (64 / 96 / 128 / 256: 0.192 / 0.186 / 0.185 / 0.199 ms on C2)
 #define FMCW_CHAIN_NT(NT)                                                  \
   do {                                                                     \
     if (p.nts_fft <= 64) return launch_chain_variant<1, NT>(p, sms, st);   \

@@ -500,23 +500,16 @@ bool chain_warp_supported(const ChainParams& p) {
 
 cudaError_t launch_frame_chain_warp(const ChainParams& p, cudaStream_t st) {
   if (p.n_frames == 0) return cudaSuccess;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int sms = device_sm_count();
   const int nz = p.nts_fft <= 64 ? 1 : p.nts_fft <= 128 ? 2 : 4;
   const bool exact = p.NTS == (uint32_t)(64 * nz) && (p.PN & 3u) == 0 && p.spec_out == nullptr;
-  static int minb = 0;
-  if (!minb) { const char* v = getenv("FMCW_CHAIN_MINB"); minb = (v && atoi(v) == 4) ? 4 : 3; }
+  static const int minb = env_int("FMCW_CHAIN_MINB", 3) == 4 ? 4 : 3;
 #define FMCW_WF(NZ_)                                                                                        \
   do {                                                                                                      \
     if (minb == 4 && NZ_ != 4)                                                                              \
       return exact ? launch_variant<NZ_, true, (NZ_ == 4 ? 3 : 4)>(p, sms, st) : launch_variant<NZ_, false, (NZ_ == 4 ? 3 : 4)>(p, sms, st); \
     return exact ? launch_variant<NZ_, true, 3>(p, sms, st) : launch_variant<NZ_, false, 3>(p, sms, st);    \
   } while (0)
-  static int nwarps = 0;
-  if (!nwarps) { const char* v = getenv("FMCW_CHAIN_WARPS"); nwarps = v ? atoi(v) : 4; }
-  if (nz == 2 && exact && nwarps == 5) return launch_variant<2, true, 3, 5>(p, sms, st);
-  if (nz == 2 && exact && nwarps == 6) return launch_variant<2, true, 3, 6>(p, sms, st);
-  if (nz == 2 && exact && nwarps == 8) return launch_variant<2, true, 2, 8>(p, sms, st);
   if (nz == 1) FMCW_WF(1);
   if (nz == 2) FMCW_WF(2);
   FMCW_WF(4);

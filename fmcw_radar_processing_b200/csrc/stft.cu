@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          uint32_t PN, unsigned long long L_total_host,
                                                          unsigned long long sample_offset,
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
-                                                         int n_chunks_req, int coef_rows, const double* __restrict__ gathered,
+                                                         int n_chunks_req, int coef_rows, const double* gathered_,
                                                          uint32_t world, uint32_t rank, sig_t* __restrict__ xc, int spec_mode,
                                                          const unsigned long long* wait_flags, unsigned long long wait_step) {
   __shared__ int s_scan[1024];
@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
   __shared__ int s_valid;
   __shared__ int s_hit;
   __shared__ unsigned long long s_lay[4];   // L_total, L_local, L_avail, sample_offset of this pass
+  // the shard headers: an all-gathered buffer, or this rank's mailbox that PEER GPUs write while this kernel runs --
+  // volatile loads after the flag's acquire, never the read-only (ld.global.nc) path
+  const volatile double* gathered = gathered_;
   StftPlan* P = t.plan;
   if (wait_flags) {
     // mailbox path: the shard headers arrive by peer stores; wait for the flag of every rank (mailbox.cu)
@@ -909,15 +912,10 @@ cudaError_t launch_stft_set_max_dev(const StftTables& t, const double* src, cuda
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static int sm_count() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  return sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 int stft_variant() {
-  static int variant = -2;
-  if (variant == -2) { const char* v = getenv("FMCW_STFT_VARIANT"); variant = v ? atoi(v) : -1; }
+  static const int variant = env_int("FMCW_STFT_VARIANT", -1);
   return variant;
 }
 
@@ -963,6 +961,87 @@ static cudaError_t launch_main_variant(const StftTables& t, const StftGeom& g, c
     if (e != cudaSuccess) return e;
     stft_main_kernel<HALF, CPT, QF, 1, THREADS, MINB><<<sms * MINB, THREADS, base, st>>>(t, g, x, out, capacity_cols, ld_cols, d_err);
   }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fine-grid PSD band (RP:283 restricted to rows first_bin + i*bin_step): what surf(T, F, psd) at RP:333 draws between its
+// ylim.  Float64 DTFT like stft_precise_kernel (a CTA owns 128 columns, their windowed taps in shared memory, cos / sin of a
+// tile of 8 rows by sincospi of the exactly reduced argument); one-sided doubling (RP:276) and the 1/max(P) of the plan.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stft_finegrid_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x,
+                                                            float* __restrict__ psd, unsigned long long first_bin,
+                                                            unsigned long long bin_step, unsigned n_rows,
+                                                            unsigned long long capacity_cols, int* d_err) {
+  const StftPlan* P = t.plan;
+  if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
+  constexpr int BT = 8, NC = 128;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int win = (int)g.win;
+  double* s_y = reinterpret_cast<double*>(s_raw);               // [win][NC] windowed, normalised taps
+  double* s_cs = s_y + (size_t)win * NC;                        // [win][2*BT] cos | sin of (n - c) * w for 8 rows
+  const int tid = threadIdx.x;
+  const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
+  const unsigned long long ncl = ce - cb;
+  if (ncl > capacity_cols) { if (tid == 0 && blockIdx.x == 0) *d_err = -4; return; }
+  const unsigned long long nfft = P->nfft;
+  const double inv = 1.0 / sqrt(P->pmax_raw);
+  const unsigned long long n_blk = (ncl + NC - 1) / NC;
+  for (unsigned long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+    unsigned long long col = cb + blk * NC + tid;
+    const bool act = col < ce;
+    if (!act) col = ce - 1;
+    __syncthreads();
+    const sig_t* xs = x + (col * g.hop - off);
+    for (int n = 0; n < win; ++n) s_y[(size_t)n * NC + tid] = t.win_d[n] * inv * xs[n];
+    for (unsigned r0 = 0; r0 < n_rows; r0 += BT) {
+      __syncthreads();
+      for (int i = tid; i < win * BT; i += NC) {
+        const int n = i / BT, j = i - n * BT;
+        double sv = 0.0, cv = 0.0;
+        if (r0 + j < n_rows) {
+          const unsigned long long bin = first_bin + (unsigned long long)(r0 + j) * bin_step;
+          const unsigned long long r = ((unsigned long long)n * bin) % nfft;      // exact reduction of n * bin / nfft turns
+          sincospi(2.0 * (double)r / (double)nfft, &sv, &cv);
+        }
+        s_cs[(size_t)n * 2 * BT + j] = cv;
+        s_cs[(size_t)n * 2 * BT + BT + j] = sv;
+      }
+      __syncthreads();
+      double re[BT], im[BT];
+#pragma unroll
+      for (int j = 0; j < BT; ++j) { re[j] = 0.0; im[j] = 0.0; }
+      for (int n = 0; n < win; ++n) {
+        const double y = s_y[(size_t)n * NC + tid];
+        const double* cs = s_cs + (size_t)n * 2 * BT;
+#pragma unroll
+        for (int j = 0; j < BT; ++j) { re[j] = fma(y, cs[j], re[j]); im[j] = fma(y, cs[BT + j], im[j]); }
+      }
+      if (act) {
+        float* dst = psd + (col - cb) * (unsigned long long)n_rows + r0;
+#pragma unroll
+        for (int j = 0; j < BT; ++j) {
+          if (r0 + j < n_rows) {
+            const unsigned long long bin = first_bin + (unsigned long long)(r0 + j) * bin_step;
+            const float cdb = (bin == 0 || bin == nfft / 2) ? 0.f : K_DB;
+            dst[j] = fmaf(K_DB, lg2_approx((float)fma(re[j], re[j], im[j] * im[j])), cdb);
+          }
+        }
+      }
+    }
+  }
+}
+
+cudaError_t launch_stft_finegrid(const StftTables& t, const StftGeom& g, const sig_t* x, float* psd, unsigned long long first_bin,
+                                 unsigned long long bin_step, unsigned n_rows, unsigned long long capacity_cols, int* d_err,
+                                 cudaStream_t st) {
+  const size_t smem = ((size_t)g.win * 128 + (size_t)g.win * 16) * sizeof(double);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(stft_finegrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  stft_finegrid_kernel<<<sm_count() * per_sm, 128, smem, st>>>(t, g, x, psd, first_bin, bin_step, n_rows, capacity_cols, d_err);
   return cudaGetLastError();
 }
 

@@ -506,10 +506,8 @@ static cudaError_t launch_tc(const StftTables& t, const StftGeom& g, const sig_t
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
                                 unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev) {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  static int dbg = -1;
-  if (dbg < 0) { const char* v = getenv("FMCW_TC_DEBUG"); dbg = v ? atoi(v) : 0; }
+  const int sms = device_sm_count();
+  static const int dbg = env_int("FMCW_TC_DEBUG", 0);
 #define FMCW_TC_ARGS t, g, x, out, tcB, capacity_cols, ld_cols, d_err, st, gmax_dev, sms, dbg
   if (layout != 0) return launch_tc<1, 0>(FMCW_TC_ARGS);
   // the fast path stores 64-bit pairs: 1,024 queries and an 8-byte aligned spectrogram

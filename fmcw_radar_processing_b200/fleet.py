@@ -66,3 +66,44 @@ class Fleet:
         for s in self._streams:
             cur.wait_stream(s)
         return results
+
+
+class AllRx:
+    """``rx_select = all``: every RX antenna of a recording as its own stream.  The reference reads RX 1
+    only (RP:202); here one handle per antenna (its own calibration table, slow-time history, ``nfft`` and normalisation
+    maximum) works on the SAME frame buffer, each on its own stream, so a 3-RX recording is processed as 3x the frames."""
+
+    def __init__(self, cfg: dict, calib, device: int = 0):
+        self.n_rx = int(cfg["num_Rx_antennas"])
+        self.fleet = None
+        self.handles = []
+        for r in range(self.n_rx):
+            c = dict(cfg)
+            c["rx_select"] = r + 1
+            self.handles.append(FmcwCuda(c, calib, device=device, torch_stream_sync=False))
+
+    def close(self):
+        for h in self.handles:
+            h.close()
+        self.handles = []
+
+    def run(self, iq, layout: int = 0):
+        """``iq``: int16 ``[n][rx][PN][NTS][2]``, NumPy (host) or a CUDA tensor.  Returns one dict per RX."""
+        res = []
+        if hasattr(iq, "is_cuda"):
+            import torch
+            cur = torch.cuda.current_stream(iq.device)
+            streams = [torch.cuda.ExternalStream(h.stream, device=iq.device) for h in self.handles]
+            for s in streams:
+                s.wait_stream(cur)
+            outs = [h.run(iq, layout=layout) for h in self.handles]          # enqueued back to back, overlapping on the device
+            for h, s, (out, inten) in zip(self.handles, streams, outs):
+                info = h.info()
+                cur.wait_stream(s)
+                res.append(dict(out, intensity=inten, info=info, ncol=info["ncol_local"]))
+        else:
+            for h in self.handles:
+                out, inten = h.run(iq, layout=layout)
+                info = h.info()
+                res.append(dict(out, intensity=inten, info=info, ncol=info["ncol_local"]))
+        return res

@@ -12,76 +12,72 @@ import math
 
 import numpy as np
 
-FMT64 = "%.15g"     # jsonencode prints doubles with 15 significant digits
-FMT32 = "%.9g"      # values that are float32 in the library (round-trips a float32)
+# ONE number format everywhere: the shortest text that round-trips the stored type (float64, or float32 for the arrays the
+# library keeps in float32), which is what std::to_chars writes in the native writer and what current MATLAB releases'
+# jsonencode prints for doubles (0.1 + 0.2 -> 0.30000000000000004).  Every numeric array goes through the native writer
+# (csrc/json_writer.cu, host-only, multi-threaded); the Python formatter below is used for 1 x 1 values and only stands in
+# for arrays when libfmcw_cuda.so is not built.
 
 
-def _fmt_for(a: np.ndarray) -> str:
-    return FMT32 if a.dtype == np.float32 else FMT64
-
-
-def _num(v, fmt) -> str:
-    v = float(v)
-    if math.isnan(v) or math.isinf(v):
+def _num(v) -> str:
+    """A scalar: integers print without a fraction, everything else in shortest round-trip form."""
+    f32 = isinstance(v, np.float32)
+    x = float(v)
+    if math.isnan(x) or math.isinf(x):
         return "null"
-    if v == int(v) and abs(v) < 1e15:
-        return str(int(v))
-    return fmt % v
+    if x == int(x) and abs(x) < 1e15:
+        return str(int(x))
+    return str(v) if f32 else repr(x)
 
 
-def _row(a: np.ndarray, fmt: str) -> str:
-    if a.size == 0:
-        return "[]"
-    if np.isfinite(a).all():
-        txt = np.char.mod(fmt, a)
-        return "[" + ",".join(txt.tolist()) + "]"
-    return "[" + ",".join(_num(v, fmt) for v in a) + "]"
+def _row(a: np.ndarray) -> str:
+    return "[" + ",".join(_num(v) for v in a) + "]"
 
 
 def write_value(f: io.TextIOBase, v):
-    """jsonencode(v) for str, scalars, vectors and 2-D matrices."""
+    """jsonencode(v) for str, scalars, vectors and 2-D matrices, in Python."""
     if isinstance(v, str):
         f.write(json.dumps(v))
         return
     a = np.asarray(v)
     if a.dtype.kind in "iub":
         a = a.astype(np.float64)
-    fmt = _fmt_for(a)
     if a.ndim == 0 or a.size == 1 and a.ndim <= 2:
-        f.write(_num(a.reshape(-1)[0], fmt))          # 1x1 -> scalar
+        f.write(_num(a.reshape(-1)[0]))               # 1x1 -> scalar
     elif a.ndim == 1 or 1 in a.shape:
-        f.write(_row(a.reshape(-1), fmt))             # row or column vector -> flat array
+        f.write(_row(a.reshape(-1)))                  # row or column vector -> flat array
     else:
-        f.write("[")
-        for i in range(a.shape[0]):                   # row-major nesting
-            if i:
-                f.write(",")
-            f.write(_row(a[i], fmt))
-        f.write("]")
+        f.write("[" + ",".join(_row(a[i]) for i in range(a.shape[0])) + "]")     # row-major nesting
 
 
-NATIVE_MIN_ELEMS = 1 << 16      # larger float matrices go through the native multi-threaded writer
+USE_NATIVE = True               # tests switch it off to compare the two writers
 
 
 def _native_append(path: str, a: np.ndarray) -> bool:
     """Appends jsonencode(a) with libfmcw_cuda's host-side writer (no GPU involved); False if unavailable."""
+    if not USE_NATIVE:
+        return False
     try:
         from . import _lib
         lib = _lib.load()
     except Exception:
         return False
-    if a.dtype not in (np.float32, np.float64) or a.ndim != 2:
+    if a.dtype.kind in "iub":
+        a = a.astype(np.float64)
+    if a.dtype not in (np.float32, np.float64) or a.ndim > 2 or a.size <= 1:
         return False
+    if a.ndim == 1:
+        a = a[None, :]
     fn = lib.fmcw_json_append_f32 if a.dtype == np.float32 else lib.fmcw_json_append_f64
     es = a.itemsize
     if a.strides[0] % es or a.strides[1] % es:
-        return False
+        a = np.ascontiguousarray(a)
     return fn(path.encode(), a.ctypes.data, a.shape[0], a.shape[1], a.strides[0] // es, a.strides[1] // es, 1) == 0
 
 
 def write_struct(path: str, fields) -> None:
-    """jsonencode(struct) with ``fields`` an ordered list of (name, value).  Large float matrices (the spectrogram,
-    the range-FFT heat map) are streamed by the native writer, everything else by Python."""
+    """jsonencode(struct) with ``fields`` an ordered list of (name, value); numeric arrays are streamed by the native
+    writer (the spectrogram payload is gigabytes of text at the reference's hop 1)."""
     f = open(path, "w")
     try:
         f.write("{")
@@ -89,13 +85,14 @@ def write_struct(path: str, fields) -> None:
             if i:
                 f.write(",")
             f.write(json.dumps(k) + ":")
-            a = v if isinstance(v, np.ndarray) else None
-            if a is not None and a.ndim == 2 and a.size >= NATIVE_MIN_ELEMS and 1 not in a.shape:
-                f.close()
-                ok = _native_append(path, a)
-                f = open(path, "a")
-                if ok:
-                    continue
+            if isinstance(v, (np.ndarray, list, tuple)) and not isinstance(v, str):
+                a = np.asarray(v)
+                if a.dtype.kind in "fiub" and a.size > 1:
+                    f.close()
+                    ok = _native_append(path, a)
+                    f = open(path, "a")
+                    if ok:
+                        continue
             write_value(f, v)
         f.write("}")
     finally:
@@ -143,3 +140,35 @@ def batch_spectrogram_payload(T, frequency, intensity, batch, start_frame, end_f
     return [("time", T), ("frequency", frequency), ("intensity", intensity),
             ("title", f"Spectrogram - Batch {batch}"), ("xLabel", "Time (s) (relative to detected activity)"),
             ("yLabel", "Frequency (Hz)"), ("start_frame", start_frame), ("end_frame", end_frame), ("filename_base", filename)]
+
+
+def _jet(x):
+    """MATLAB's jet colormap at x in [0, 1] -> uint8 RGB."""
+    r = np.clip(np.minimum(4 * x - 1.5, -4 * x + 4.5), 0, 1)
+    g = np.clip(np.minimum(4 * x - 0.5, -4 * x + 3.5), 0, 1)
+    b = np.clip(np.minimum(4 * x + 0.5, -4 * x + 2.5), 0, 1)
+    return (np.stack([r, g, b], axis=-1) * 255 + 0.5).astype(np.uint8)
+
+
+def write_spectrogram_png(path, psd_band, clim=(-40.0, 0.0), max_width=3600):
+    """spectrogram.png (RP:332-348): ``psd_band`` [ncol][n_rows] is psd on the fine-grid rows between ylim [0 150] Hz
+    (fmcw_stft_finegrid); view(0, 90), axis off, colormap(jet), clim [-40 0].  Frequency runs upwards, time to the right;
+    at most ``max_width`` columns (6 in x 600 dpi, RP:344).  A plain 8-bit RGB PNG written with zlib -- the rendering of
+    MATLAB's surf / exportgraphics is not reproduced pixel for pixel (out of scope)."""
+    import struct
+    import zlib
+    a = np.asarray(psd_band, dtype=np.float32)
+    step = max(1, -(-a.shape[0] // max_width))
+    img = a[::step].T[::-1]                                    # rows = frequency (top = f_hi), columns = time
+    x = (np.nan_to_num(img, nan=clim[0], neginf=clim[0], posinf=clim[1]) - clim[0]) / (clim[1] - clim[0])
+    rgb = _jet(np.clip(x, 0, 1))
+    h, w, _ = rgb.shape
+    raw = np.concatenate([np.zeros((h, 1), dtype=np.uint8), rgb.reshape(h, w * 3)], axis=1).tobytes()
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+    return w, h

@@ -38,6 +38,11 @@ def send_json_string_to_blob_storage(filename):
     uploaded.append(os.path.basename(filename))
 
 
+def send_picture_to_blob_storage(filename):
+    """SP:1-80 stubbed to a local file (the PNG stays in the working directory)."""
+    return filename
+
+
 def _speed(cfg, doppler_bin):
     # RP:250 with tgt_doppler_idx = doppler_bin + 1
     return (doppler_bin + 1 - cfg["Doppler_fft_size"] / 2 - 1) * -cfg["fD_per_bin"] * cfg["Hz_to_mps_constant"]
@@ -89,6 +94,12 @@ def _branch_no(h, cfg, frame, N, filename, workdir, result):
     cfg["max_slider_index"] = ncol - cfg["window_length"]            # RP:287
     intensity = inten[:ncol].T                                       # 1024 x ncol view
     _write(workdir, "spectrogram_data.json", payloads.spectrogram_payload(T, F, intensity), result)      # RP:307-328
+    # RP:332-348: spectrogram.png = surf(T, F, psd) between ylim [0 150], clim [-40 0], jet -- from the fine-grid band, not
+    # from the 671 GB matrix P
+    band, _ = h.stft_finegrid(0.0, 150.0, max_rows=2400)
+    payloads.write_spectrogram_png(os.path.join(workdir, "spectrogram.png"), band)
+    send_picture_to_blob_storage(os.path.join(workdir, "spectrogram.png"))
+    result["files"].append("spectrogram.png")
     _write(workdir, filename + "_range_fft_data.json",
            payloads.range_fft_payload(N, array_bin_range(cfg), out["range_max_abs"].T, filename), result)  # RP:355-377
     rng = np.where(det, out["range_bin"] * cfg["dist_per_bin"], 0.0)                                     # RP:248

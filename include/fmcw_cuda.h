@@ -7,6 +7,7 @@
  *   RP:270-299  STFT + dB + log-frequency resample -> fmcw_stft / fmcw_run
  *   RP:457-566  same per 100-frame batch ('yes')   -> fmcw_run on a frame sub-range
  *   RP:410-411  range spectrum of one (frame,chirp)-> fmcw_range_spectrum
+ *   RP:332-348  fine-grid psd band of the picture  -> fmcw_stft_finegrid
  *   RP:89-179   configuration                      -> fmcw_config (fmcw_configurations, RP:645-672)
  * The reference has no FFI of its own (pure MATLAB); the MEX gateway (mex/) and the
  * Node-API addon (node/) bind exactly these entry points, see INTEGRATION.md.
@@ -220,6 +221,18 @@ FMCW_API fmcw_status fmcw_mailbox_stft(fmcw_handle* h, void* const* mailboxes, u
  * log_freq_bins (RP:293-296).  Either pointer may be NULL. */
 FMCW_API fmcw_status fmcw_stft_axes(const fmcw_config* cfg, uint64_t L_total, uint64_t col_begin, uint64_t ncol,
                                     double* time, double* frequency, uint64_t* nfft, uint64_t* ncol_total);
+
+/* Fine-grid PSD band for the spectrogram picture (RP:332-348: surf(T, F, psd), ylim [0 150], clim [-40 0]) of the signal of
+ * the last fmcw_run / fmcw_stft_frames / fmcw_stft call: psd = 20*log10(P / max(P)) (RP:283) at the one-sided fine-grid bins
+ * F_j = j*fs/nfft inside [f_lo_hz, f_hi_hz], every `*bin_step`-th bin so that at most max_rows rows come back (a 5,000-frame
+ * recording has 62,915 fine-grid bins below 150 Hz; the literal psd matrix of RP:283 is 671 GB).  psd: [ncol][n_rows] floats,
+ * time-major = MATLAB's column-major psd(rows, cols) restricted to the selected rows; host or device memory with room for
+ * capacity_cols columns of max_rows rows.  first_bin / bin_step / n_rows / ncol describe the rows and columns written
+ * (F = (first_bin + i*bin_step)*fs/nfft; the time axis is fmcw_stft_axes').  Single-GPU runs only (local columns of a
+ * sharded run are returned as they are, normalised by the global maximum). */
+FMCW_API fmcw_status fmcw_stft_finegrid(fmcw_handle* h, double f_lo_hz, double f_hi_hz, uint32_t max_rows, float* psd,
+                                        uint64_t capacity_cols, uint64_t* first_bin, uint64_t* bin_step, uint64_t* n_rows,
+                                        uint64_t* ncol);
 
 /* Range spectrum abs(range_fft(:, chirp)) of one frame (RP:410-411). out: [range_fft_size] floats. */
 FMCW_API fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,

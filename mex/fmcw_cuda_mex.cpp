@@ -30,10 +30,18 @@ fmcw_handle* g_handle = nullptr;
 fmcw_config g_cfg;
 bool g_have_cfg = false;
 
-void at_exit() {
+bool g_locked = false;
+
+// Destroys the handle and releases the lock taken when it was created, so that `clear fmcw_cuda_mex` works again once no
+// handle is alive (one mexLock per live handle, never more: mexLock counts).
+void release_handle() {
   if (g_handle) fmcw_destroy(g_handle);
   g_handle = nullptr;
+  g_have_cfg = false;
+  if (g_locked) { mexUnlock(); g_locked = false; }
 }
+
+void at_exit() { release_handle(); }
 
 double field(const mxArray* s, const char* name, double dflt, bool required, std::string& missing) {
   const mxArray* f = mxGetField(s, 0, name);
@@ -69,19 +77,21 @@ bool read_config(const mxArray* s, fmcw_config& c, std::string& missing) {
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   std::string err_id, err_msg;   // filled instead of throwing; reported after all C++ state is consistent
   do {
-    if (nrhs != 4 || !mxIsChar(prhs[0]) || !mxIsStruct(prhs[3])) { err_id = "fmcw:usage"; err_msg = "out = fmcw_cuda_mex(cmd, data, calib_data, cfg)"; break; }
+    if (nrhs < 1 || !mxIsChar(prhs[0])) { err_id = "fmcw:usage"; err_msg = "out = fmcw_cuda_mex(cmd, data, calib_data, cfg)"; break; }
     char cmd[16] = {0};
     mxGetString(prhs[0], cmd, sizeof(cmd));
+    if (std::strcmp(cmd, "release") == 0) { release_handle(); plhs[0] = mxCreateDoubleScalar(0.0); break; }   // fmcw_cuda_mex('release'): frees the GPU state, unlocks the MEX file
+    if (nrhs != 4 || !mxIsStruct(prhs[3])) { err_id = "fmcw:usage"; err_msg = "out = fmcw_cuda_mex(cmd, data, calib_data, cfg)"; break; }
     fmcw_config c;
     std::string missing;
     if (!read_config(prhs[3], c, missing)) { err_id = "fmcw:config"; err_msg = "cfg is missing field " + missing; break; }
     if (!g_handle || !g_have_cfg || std::memcmp(&c, &g_cfg, sizeof(c)) != 0) {
-      at_exit();
+      release_handle();
       const double* cal = mxIsDouble(prhs[2]) ? mxGetPr(prhs[2]) : nullptr;
       fmcw_status st = fmcw_create(&c, cal, cal ? (uint64_t)mxGetNumberOfElements(prhs[2]) : 0, 0, &g_handle);
       if (st != FMCW_OK) { err_id = "fmcw:create"; err_msg = fmcw_status_string(st); g_handle = nullptr; break; }
       g_cfg = c; g_have_cfg = true;
-      mexLock();
+      if (!g_locked) { mexLock(); g_locked = true; }
       mexAtExit(at_exit);
     }
     const uint32_t NTS = c.num_ADC_samples_per_chirp, PN = c.num_chirps_per_frame, ND = c.Doppler_fft_size, NQ = c.MAX_FREQ_BINS;

@@ -22,7 +22,7 @@ mxArray* mxCreateNumericMatrix(mwSize, mwSize, mxClassID, mxComplexity);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateDoubleScalar(double);
 void mxSetN(mxArray*, mwSize);
-void mexLock(void); int mexAtExit(void (*)(void));
+void mexLock(void); void mexUnlock(void); int mexAtExit(void (*)(void));
 void mexErrMsgIdAndTxt(const char*, const char*, ...);
 void mexFunction(int, mxArray*[], int, const mxArray*[]);
 #ifdef __cplusplus

@@ -61,10 +61,18 @@ struct Wrapped { fmcw_handle* h; fmcw_config cfg; };
 napi_value Create(napi_env env, napi_callback_info info) {
   size_t argc = 2; napi_value argv[2];
   napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  if (argc < 1) { napi_throw_error(env, "FMCW_USAGE", "create(cfg [, calibFloat64Array])"); return nullptr; }
   Wrapped* w = new Wrapped();
   fill_config(env, argv[0], w->cfg);
   void* cal = nullptr; size_t cal_len = 0; napi_typedarray_type ty; napi_value ab; size_t off;
-  if (argc > 1) napi_get_typedarray_info(env, argv[1], &ty, &cal_len, &cal, &ab, &off);
+  if (argc > 1) {
+    // the calibration vector is read as doubles: anything but a Float64Array is rejected, not reinterpreted
+    if (napi_get_typedarray_info(env, argv[1], &ty, &cal_len, &cal, &ab, &off) != napi_ok || ty != napi_float64_array) {
+      delete w;
+      napi_throw_error(env, "FMCW_TYPE", "calibration data must be a Float64Array");
+      return nullptr;
+    }
+  }
   fmcw_status st = fmcw_create(&w->cfg, (const double*)cal, cal_len, 0, &w->h);
   if (st != FMCW_OK) { delete w; napi_throw_error(env, "FMCW_CREATE", fmcw_status_string(st)); return nullptr; }
   napi_value ext;
@@ -141,14 +149,33 @@ void Complete(napi_env env, napi_status, void* data) {   // back on the JS threa
 napi_value Run(napi_env env, napi_callback_info info) {
   size_t argc = 3; napi_value argv[3];
   napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  if (argc < 3) { napi_throw_error(env, "FMCW_USAGE", "run(handle, iqInt16Array, nFrames)"); return nullptr; }
   Wrapped* w = nullptr;
-  napi_get_value_external(env, argv[0], (void**)&w);
+  if (napi_get_value_external(env, argv[0], (void**)&w) != napi_ok || !w || !w->h) {
+    napi_throw_error(env, "FMCW_HANDLE", "invalid or destroyed handle");
+    return nullptr;
+  }
+  void* data = nullptr; size_t len = 0; napi_typedarray_type ty; napi_value ab; size_t off;
+  if (napi_get_typedarray_info(env, argv[1], &ty, &len, &data, &ab, &off) != napi_ok || ty != napi_int16_array) {
+    napi_throw_error(env, "FMCW_TYPE", "iq must be an Int16Array [frame][rx][chirp][sample][I,Q]");
+    return nullptr;
+  }
+  double n = 0;
+  if (napi_get_value_double(env, argv[2], &n) != napi_ok || !(n >= 0) || n != (double)(uint64_t)n) {
+    napi_throw_error(env, "FMCW_SIZE", "nFrames must be a non-negative integer");
+    return nullptr;
+  }
+  // fmcw_run reads n * RX * PN * NTS (I,Q) pairs: never past the ArrayBuffer
+  const fmcw_config& wc = w->cfg;
+  const double per_frame = 2.0 * wc.num_Rx_antennas * wc.num_chirps_per_frame * wc.num_ADC_samples_per_chirp;
+  if (n * per_frame > (double)len) {
+    napi_throw_error(env, "FMCW_SIZE", "iq holds fewer than nFrames frames of the configured shape");
+    return nullptr;
+  }
   Job* j = new Job();
   j->h = w->h; j->cfg = w->cfg;
-  void* data; size_t len; napi_typedarray_type ty; napi_value ab; size_t off;
-  napi_get_typedarray_info(env, argv[1], &ty, &len, &data, &ab, &off);
   j->iq = (const int16_t*)data;
-  double n = 0; napi_get_value_double(env, argv[2], &n); j->n = (uint64_t)n;
+  j->n = (uint64_t)n;
   napi_create_reference(env, argv[1], 1, &j->iq_ref);     // keep the input alive while the pool thread reads it
   napi_value promise, name;
   napi_create_promise(env, &j->deferred, &promise);

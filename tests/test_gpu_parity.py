@@ -339,3 +339,24 @@ def test_handle_is_not_reentrant(api):
     e_db, _ = H.spectrogram_errors(inten[:nc].T, ref["stft"]["intensity"])
     assert e_db < TOL_DB
     h.close()
+
+
+def test_finegrid_psd_band_matches_literal(api):
+    """fmcw_stft_finegrid: the rows of psd = 20*log10(P/max(P)) (RP:283) that surf(T, F, psd) draws between ylim [0 150]
+    (RP:333-336), against the literal one-sided P of the oracle; and the decimated form picks exactly every step-th row."""
+    case = H.make_case(n_frames=6, NTS=128, PN=64)
+    ref = H.oracle_no(case, stft="literal")
+    lit = ref["stft"]
+    h = api(case["cfg"], case["calib"])
+    h.run(case["iq"])
+    psd, F = h.stft_finegrid(0.0, 150.0, max_rows=4096)
+    nfft, fs = lit["nfft"], 1.0 / case["cfg"]["PRT"]
+    rows = np.flatnonzero(np.arange(nfft // 2 + 1) * fs / nfft <= 150.0 + 1e-9)
+    assert psd.shape == (lit["P"].shape[1], rows.size) and np.allclose(F, rows * fs / nfft, rtol=1e-14)
+    with np.errstate(divide="ignore"):
+        want = 20 * np.log10(lit["P"][rows, :] / lit["pmax"])
+    H.assert_spectrogram_contract(psd.T, want, precise=True)
+    small, F2 = h.stft_finegrid(0.0, 150.0, max_rows=16)
+    step = -(-rows.size // 16)
+    assert small.shape[1] == -(-rows.size // step) and np.array_equal(small, psd[:, ::step]) and np.allclose(F2, F[::step])
+    h.close()

@@ -50,6 +50,18 @@ def test_no_branch_payloads_match_oracle(tmp_path):
     assert np.allclose(np.array(rs["speed"])[:, 0], ref["speed"], rtol=1e-14, atol=0)
     ff = json.load(open(tmp_path / "radar_data_fft_data.json"))
     assert ff["frame_index"] == 100 and ff["range_bins"] == list(range(256)) and len(ff["magnitude"]) == 256
+    # RP:332-348: spectrogram.png from the fine-grid psd band (0-150 Hz, clim [-40 0], jet)
+    import struct
+    import zlib
+    png = open(tmp_path / "spectrogram.png", "rb").read()
+    assert png[:8] == b"\x89PNG\r\n\x1a\n" and png[12:16] == b"IHDR"
+    w, hgt = struct.unpack(">II", png[16:24])
+    assert w == 28 * 64 - 19 and 100 < hgt <= 2400
+    ilen = struct.unpack(">I", png[33:37])[0]
+    raw = zlib.decompress(png[41:41 + ilen])
+    assert len(raw) == hgt * (1 + 3 * w)
+    px = np.frombuffer(raw, dtype=np.uint8).reshape(hgt, 1 + 3 * w)[:, 1:].reshape(hgt, w, 3)
+    assert (px[-1, :, 0] > 100).mean() > 0.9       # the bottom row (lowest frequencies) is the hot end of jet: red
 
 
 def test_no_branch_without_any_target_is_a_failed_step(tmp_path):
@@ -294,3 +306,24 @@ def test_fleet_of_radars_equals_one_by_one():
     assert got[2]["info"]["n_detected"] == 0 and got[2]["ncol"] == 0
     h.close()
     fleet.close()
+
+
+def test_all_rx_streams_match_the_oracle_per_antenna():
+    """rx_select = all: one stream per antenna on the same frame buffer; antenna r equals the oracle run on
+    that antenna, from host buffers and from a device tensor."""
+    import torch
+    from fmcw_radar_processing_b200.fleet import AllRx
+    case = H.make_case(n_frames=16, NTS=128, PN=64, n_rx=3)
+    a = AllRx(case["cfg"], case["calib"])
+    res_h = a.run(case["iq"])
+    res_d = a.run(torch.from_numpy(case["iq"]).cuda())
+    for r in range(3):
+        ref = H.oracle_no(case, rx_select=r + 1)
+        for res in (res_h, res_d):
+            out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res[r].items() if k not in ("info",)}
+            d = ref["detected"]
+            assert np.array_equal(out["detected"].astype(bool), d) and np.array_equal(out["range_bin"][d], ref["range_idx"][d] - 1)
+            nc = res[r]["ncol"]
+            H.assert_spectrogram_contract(out["intensity"][:nc].T, ref["stft"]["intensity"])
+    assert not np.array_equal(res_h[0]["intensity"][:100], res_h[1]["intensity"][:100])      # the antennas differ (phase offset)
+    a.close()

@@ -52,9 +52,10 @@ def test_jsonencode_conventions(tmp_path):
     d = json.loads(txt)
     assert list(d) == ["row", "col", "mat", "one", "s", "f32"]                   # field order
     assert d["row"] == [0, 1, 2] and d["col"] == [0, 1, 2]                       # vectors flatten
-    assert d["mat"] == [[1, None], [None, 0.3]]                                  # row-major nesting, NaN/Inf -> null, 15 digits
+    assert d["mat"] == [[1, None], [None, 0.1 + 0.2]]                            # row-major nesting, NaN/Inf -> null, shortest round trip
+    assert '0.30000000000000004' in txt                                          # what MATLAB's jsonencode prints for 0.1 + 0.2
     assert d["one"] == 5 and d["s"] == "radar_data"
-    assert '"f32":[0.100000001,0.25]' in txt
+    assert '"f32":[0.1,0.25]' in txt                                             # float32 values in THEIR shortest round-trip form
 
 
 def test_range_speed_growing_matrix_quirk():
@@ -110,14 +111,12 @@ def test_native_json_writer_matches_python_writer(tmp_path):
     d = rng.standard_normal((260, 256))
     fields = [("time", np.arange(5) * 0.15), ("intensity", view), ("m64", d), ("title", "x")]
     p_native, p_py = str(tmp_path / "n.json"), str(tmp_path / "p.json")
-    old = P.NATIVE_MIN_ELEMS
     try:
-        P.NATIVE_MIN_ELEMS = 1
         P.write_struct(p_native, fields)
-        P.NATIVE_MIN_ELEMS = 1 << 60
+        P.USE_NATIVE = False
         P.write_struct(p_py, fields)
     finally:
-        P.NATIVE_MIN_ELEMS = old
+        P.USE_NATIVE = True
     n, p = json.load(open(p_native)), json.load(open(p_py))
     assert list(n) == list(p) == ["time", "intensity", "m64", "title"]
     assert n["intensity"][2][3] is None and n["intensity"][5][7] is None
@@ -125,4 +124,6 @@ def test_native_json_writer_matches_python_writer(tmp_path):
     m = np.isfinite(a)
     assert np.array_equal(gn[m], a[m])                      # shortest round-trip digits reproduce every float32
     assert np.allclose(np.array(n["m64"]), d, rtol=0, atol=0)
-    assert np.allclose(np.array(p["m64"]), d, rtol=1e-14)   # the Python writer prints 15 significant digits
+    assert np.array_equal(np.array(p["m64"]), d)            # the Python stand-in round-trips too
+    gp = np.array([[np.nan if v is None else v for v in r] for r in p["intensity"]], dtype=np.float32)
+    assert np.array_equal(gp[m], a[m])
