@@ -135,6 +135,14 @@ struct fmcw_handle {
   StftTables mx_key_tables{};
   const void* mx_key_xc = nullptr;
   int mx_eligible_calls = 0;
+  // mailbox path: the device-side step counter and the whole exchange pass (post heads, plan confirm, operand prepare,
+  // colstat, refine, hard, post max, collect max) as one CUDA graph
+  DevBuf mb_step;
+  unsigned long long mb_step_host = 0, mb_seed = 0;
+  cudaGraphExec_t mbx_exec = nullptr;
+  struct MbxKey { StftTables t; const void* xc; void* ptr[MAILBOX_MAX_WORLD]; uint32_t world, rank; } mbx_key{};
+  int mbx_eligible_calls = 0;
+  bool mbx_use_graph = false, mbx_collected = false;
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   std::string err;
   // chain tables
@@ -595,11 +603,12 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   h->st.hard_cap = 1u << 20;
   ok(h->hard.ensure((size_t)h->st.hard_cap * 4));
   ok(h->tcb.ensure(stft_tc_table_bytes(nb_max) + 256));
-  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16)); ok(h->gmax.ensure(16));
+  ok(h->derr.ensure(16)); ok(h->ndet.ensure(16)); ok(h->gmax.ensure(16)); ok(h->mb_step.ensure(16));
   if (e == cudaSuccess) {
     ok(cudaMemsetAsync(h->plan.p, 0, sizeof(StftPlan), h->stream));
     ok(cudaMemsetAsync(h->derr.p, 0, 16, h->stream));
     ok(cudaMemsetAsync(h->ndet.p, 0, 16, h->stream));
+    ok(cudaMemsetAsync(h->mb_step.p, 0, 16, h->stream));
     ok(cudaStreamSynchronize(h->stream));
   }
   if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? FMCW_ERR_OOM : FMCW_ERR_CUDA; cudaGetLastError(); return bail(rc); }
@@ -615,6 +624,8 @@ void fmcw_destroy(fmcw_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->side) cudaStreamSynchronize(h->side);
   if (h->mx_exec) { cudaGraphExecDestroy(h->mx_exec); h->mx_exec = nullptr; }
+  if (h->mbx_exec) { cudaGraphExecDestroy(h->mbx_exec); h->mbx_exec = nullptr; }
+  h->mb_step.release();
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->swin_d, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
                    &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->hfft_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
@@ -920,8 +931,19 @@ fmcw_status fmcw_mailbox_post_heads(fmcw_handle* h, void* const* mailboxes, uint
   MailboxSet mb;
   fmcw_status s = mailbox_args(h, mailboxes, world, rank, step, mb);
   if (s != FMCW_OK) return s;
+  // the kernels count the passes themselves; the caller's step number re-seeds the counter whenever it does not follow
+  if (step != h->mb_step_host + 1) {
+    h->mb_seed = step - 1;
+    CK(cudaMemcpyAsync(h->mb_step.p, &h->mb_seed, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream), "seed step counter");
+  }
+  h->mb_step_host = step;
+  h->mbx_collected = false;
+  static const int use_graph = env_int("FMCW_GRAPH", 1) != 0;
+  h->mbx_use_graph = use_graph && h->lookahead && ++h->mbx_eligible_calls > 1;
+  if (h->mbx_use_graph) return FMCW_OK;        // the post kernel is the first node of the graph fmcw_mailbox_plan launches
   CK(launch_mailbox_post_heads(h->xc.as<sig_t>(), h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame,
-                               h->cfg.window_length, mb, world, rank, step, h->stream), "mailbox post heads kernel");
+                               h->cfg.window_length, mb, world, rank, h->mb_step.as<unsigned long long>(), h->stream),
+     "mailbox post heads kernel");
   return FMCW_OK;
 }
 
@@ -935,14 +957,49 @@ fmcw_status fmcw_mailbox_plan(fmcw_handle* h, void* const* mailboxes, uint32_t w
   fmcw_status s = mailbox_args(h, mailboxes, world, rank, step, mb);
   if (s != FMCW_OK) return s;
   void* own = mb.ptr[rank];
+  if (step != h->mb_step_host) return fail(h, FMCW_ERR_STATE, "fmcw_mailbox_post_heads of this step must run first");
+  unsigned long long* d_step = h->mb_step.as<unsigned long long>();
   int spec_mode = 0;
   CK(join_lookahead(h, spec_mode), "join look-ahead plan");
-  CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
-                      mailbox_heads(own), world, rank, h->xc.as<sig_t>(), spec_mode, mailbox_flag_heads(own), step),
-     "stft plan kernel");
   h->mb_world = world; h->mb_rank = rank;
+  if (h->mbx_use_graph && spec_mode == 2) {
+    fmcw_handle::MbxKey key{};
+    key.t = h->st; key.xc = h->xc.p; key.world = world; key.rank = rank;
+    for (uint32_t r = 0; r < world; ++r) key.ptr[r] = mb.ptr[r];
+    if (!h->mbx_exec || memcmp(&key, &h->mbx_key, sizeof(key)) != 0) {
+      if (h->mbx_exec) { cudaGraphExecDestroy(h->mbx_exec); h->mbx_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
+      cudaError_t e1 = launch_mailbox_post_heads(h->xc.as<sig_t>(), h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame,
+                                                 h->cfg.window_length, mb, world, rank, d_step, h->stream);
+      cudaError_t e2 = launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
+                                        mailbox_heads(own), world, rank, h->xc.as<sig_t>(), 2, mailbox_flag_heads(own), d_step);
+      cudaError_t e3 = launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream, h->gmax.as<double>());
+      cudaError_t e4 = launch_mailbox_post_max(h->gmax.as<double>(), mb, world, rank, d_step, h->stream);
+      cudaError_t e5 = launch_mailbox_collect_max(own, world, d_step, h->gmax.as<double>() + 1, h->derr.as<int>(), h->stream);
+      cudaError_t e6 = cudaStreamEndCapture(h->stream, &graph);
+      CK(e1, "capture post heads"); CK(e2, "capture stft plan"); CK(e3, "capture stft max"); CK(e4, "capture post max");
+      CK(e5, "capture collect max"); CK(e6, "end capture");
+      cudaError_t e7 = cudaGraphInstantiate(&h->mbx_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      CK(e7, "instantiate graph");
+      h->mbx_key = key;
+    }
+    CK(cudaGraphLaunch(h->mbx_exec, h->stream), "launch mailbox exchange graph");
+    h->mbx_collected = true;
+    h->planned = true; h->have_info = false;
+    return FMCW_OK;
+  }
+  if (h->mbx_use_graph) {       // the look-ahead was not joined after all: post now, then the plain sequence
+    CK(launch_mailbox_post_heads(h->xc.as<sig_t>(), h->ndet.as<unsigned long long>(), h->cfg.num_chirps_per_frame,
+                                 h->cfg.window_length, mb, world, rank, d_step, h->stream), "mailbox post heads kernel");
+    h->mbx_use_graph = false;
+  }
+  CK(launch_stft_plan(h->st, h->geom, nullptr, h->cfg.num_chirps_per_frame, 0, 0, 0, 0, h->n_chunks, h->stream,
+                      mailbox_heads(own), world, rank, h->xc.as<sig_t>(), spec_mode, mailbox_flag_heads(own), d_step),
+     "stft plan kernel");
   CK(launch_stft_max(h->st, h->geom, h->xc.as<sig_t>(), h->stream, h->gmax.as<double>()), "stft max kernels");
-  CK(launch_mailbox_post_max(h->gmax.as<double>(), mb, world, rank, step, h->stream), "mailbox post max kernel");
+  CK(launch_mailbox_post_max(h->gmax.as<double>(), mb, world, rank, d_step, h->stream), "mailbox post max kernel");
   h->planned = true; h->have_info = false;
   return FMCW_OK;
 }
@@ -960,8 +1017,11 @@ fmcw_status fmcw_mailbox_stft(fmcw_handle* h, void* const* mailboxes, uint32_t w
   fmcw_status s = mailbox_args(h, mailboxes, world, rank, step, mb);
   if (s != FMCW_OK) return s;
   const uint64_t ld = sout->ld_cols ? sout->ld_cols : sout->capacity_cols;
-  CK(launch_mailbox_collect_max(mb.ptr[rank], world, step, h->gmax.as<double>() + 1, h->derr.as<int>(), h->stream),
-     "mailbox collect max kernel");
+  if (step != h->mb_step_host) return fail(h, FMCW_ERR_STATE, "fmcw_mailbox_plan of this step must run first");
+  if (!h->mbx_collected)
+    CK(launch_mailbox_collect_max(mb.ptr[rank], world, h->mb_step.as<unsigned long long>(), h->gmax.as<double>() + 1,
+                                  h->derr.as<int>(), h->stream), "mailbox collect max kernel");
+  h->mbx_collected = true;
   CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
   CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), sout->intensity, sout->capacity_cols, ld, (int)sout->layout,
                       h->derr.as<int>(), h->stream, h->gmax.as<double>() + 1, h->stft_precise), "stft main kernel");

@@ -107,7 +107,7 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
                              cudaStream_t st, const double* gathered = nullptr, uint32_t world = 0, uint32_t rank = 0,
                              sig_t* xc = nullptr, int spec_mode = 0, const unsigned long long* wait_flags = nullptr,
-                             unsigned long long wait_step = 0);
+                             const unsigned long long* wait_step = nullptr);
 cudaError_t launch_stft_max(const StftTables& t, const StftGeom& g, const sig_t* x, cudaStream_t st,
                             double* export_dst = nullptr);
 cudaError_t launch_stft_set_max(const StftTables& t, double pmax_raw, cudaStream_t st);
@@ -163,11 +163,11 @@ __device__ __forceinline__ bool mailbox_wait(const unsigned long long* flags, ui
 }
 #endif
 cudaError_t launch_mailbox_post_heads(const sig_t* xc, const unsigned long long* d_ndet, uint32_t PN, uint32_t win,
-                                      const MailboxSet& mb, uint32_t world, uint32_t rank, unsigned long long step,
+                                      const MailboxSet& mb, uint32_t world, uint32_t rank, unsigned long long* d_step,
                                       cudaStream_t st);
 cudaError_t launch_mailbox_post_max(const double* local_max, const MailboxSet& mb, uint32_t world, uint32_t rank,
-                                    unsigned long long step, cudaStream_t st);
-cudaError_t launch_mailbox_collect_max(void* own, uint32_t world, unsigned long long step, double* gmax, int* d_err,
+                                    const unsigned long long* d_step, cudaStream_t st);
+cudaError_t launch_mailbox_collect_max(void* own, uint32_t world, const unsigned long long* d_step, double* gmax, int* d_err,
                                        cudaStream_t st);
 
 // ---- synthetic scene generator ------------------------------------------------------------------

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
                                                          unsigned long long L_local_host, unsigned long long L_avail_host,
                                                          int n_chunks_req, int coef_rows, const double* gathered_,
                                                          uint32_t world, uint32_t rank, sig_t* __restrict__ xc, int spec_mode,
-                                                         const unsigned long long* wait_flags, unsigned long long wait_step) {
+                                                         const unsigned long long* wait_flags, const unsigned long long* wait_step_ptr) {
   __shared__ int s_scan[1024];
   __shared__ int s_wsum[32];
   __shared__ unsigned long long s_nfft;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(1024) stft_plan_kernel(StftTables t, StftGeom 
     __shared__ int s_late;
     if (threadIdx.x == 0) s_late = 0;
     __syncthreads();
-    if (!mailbox_wait(wait_flags, threadIdx.x, world, wait_step)) s_late = 1;
+    if (!mailbox_wait(wait_flags, threadIdx.x, world, *wait_step_ptr)) s_late = 1;
     __syncthreads();
     if (s_late) { if (threadIdx.x == 0) { P->valid = -6; P->nb = 0; P->n_chunks = 0; } return; }
   }
@@ -923,7 +923,7 @@ cudaError_t launch_stft_plan(const StftTables& t, const StftGeom& g, const unsig
                              unsigned long long L_total_host, unsigned long long sample_offset,
                              unsigned long long L_local_host, unsigned long long L_avail_host, int n_chunks,
                              cudaStream_t st, const double* gathered, uint32_t world, uint32_t rank, sig_t* xc, int spec_mode,
-                             const unsigned long long* wait_flags, unsigned long long wait_step) {
+                             const unsigned long long* wait_flags, const unsigned long long* wait_step) {
   const bool tc = (g.win == 20 && stft_variant() < 0);
   stft_plan_kernel<<<1, 1024, 0, st>>>(t, g, d_ndet, PN, L_total_host, sample_offset, L_local_host, L_avail_host, n_chunks,
                                        tc ? 2 : 0, gathered, world, rank, xc, spec_mode, wait_flags, wait_step);

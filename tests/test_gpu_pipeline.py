@@ -205,7 +205,8 @@ def test_async_sharded_path_equals_single_gpu(split):
 def test_mailbox_sharded_path_equals_single_gpu(split):
     """fmcw_mailbox_post_heads / fmcw_mailbox_plan / fmcw_mailbox_stft: the peer-memory hand-offs (headers, halo,
     offsets, global max exchanged by stores + flags inside the kernels), with the ranks emulated as handles on one
-    GPU whose mailboxes are ordinary device buffers.  Two passes in a row reuse the mailboxes (step numbers)."""
+    GPU whose mailboxes are ordinary device buffers.  Four passes in a row reuse the mailboxes (step numbers): the first
+    two launch the exchange kernels one by one, the third captures them as one CUDA graph, the fourth replays it."""
     import torch
     from fmcw_radar_processing_b200.api import FmcwCuda
     n = sum(split)
@@ -221,7 +222,7 @@ def test_mailbox_sharded_path_equals_single_gpu(split):
     boxes = [torch.zeros((hs[0].mailbox_bytes() + 7) // 8, dtype=torch.float64, device="cuda") for _ in split]
     torch.cuda.synchronize()
     ptrs = [b.data_ptr() for b in boxes]
-    for step in (1, 2):
+    for step in (1, 2, 3, 4):
         f0 = 0
         for r, (h, k) in enumerate(zip(hs, split)):
             h.process_frames(iq_d[f0:f0 + k].contiguous())
