@@ -66,6 +66,7 @@ EXPORTS = {
     "fmcw_stft_frames": (C.c_int, [C.c_void_p, C.POINTER(fmcw_stft_out)]),
     "fmcw_stft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(fmcw_stft_out)]),
     "fmcw_get_slow_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "fmcw_load_slow_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "fmcw_set_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "fmcw_stft_local_max": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]),
     "fmcw_stft_sharded": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.POINTER(fmcw_stft_out)]),

@@ -225,6 +225,10 @@ class FmcwCuda:
         self._check(self.lib.fmcw_get_slow_time(self._h, _ptr(dst), first, count))
         return dst
 
+    def load_slow_time(self, x, L_local: int, n_halo: int):
+        """Streaming: hand a piece of the caller-kept slow-time signal back (L_local samples + n_halo following ones)."""
+        self._check(self.lib.fmcw_load_slow_time(self._h, _ptr(x) if (L_local + n_halo) else None, L_local, n_halo))
+
     def set_halo(self, src, count: int):
         self._check(self.lib.fmcw_set_halo(self._h, _ptr(src) if count else None, count))
 

@@ -808,6 +808,29 @@ fmcw_status fmcw_get_slow_time(fmcw_handle* h, double* dst, uint64_t first, uint
   return FMCW_OK;
 }
 
+fmcw_status fmcw_load_slow_time(fmcw_handle* h, const double* x, uint64_t L_local, uint64_t n_halo) {
+  if (!h || (!x && (L_local || n_halo))) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  const uint32_t PN = h->cfg.num_chirps_per_frame;
+  if (L_local % PN) return fail(h, FMCW_ERR_SIZE, "L_local must be a multiple of num_chirps_per_frame");
+  if (n_halo >= h->cfg.window_length) return fail(h, FMCW_ERR_SIZE, "halo longer than window_length-1");
+  CK(h->xc.ensure((L_local + h->cfg.window_length) * sizeof(sig_t)), "alloc slow-time signal");
+  CK(h->colub.ensure((L_local + h->cfg.window_length) * 4), "alloc column bounds");
+  h->st.col_ub = h->colub.as<float>();
+  if (L_local + n_halo)
+    CK(cudaMemcpyAsync(h->xc.p, x, (L_local + n_halo) * sizeof(sig_t),
+                       is_device_ptr(x) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream), "copy slow-time samples");
+  h->n_det_host = L_local / PN;
+  h->mb_seed = 0;
+  const unsigned long long nd = h->n_det_host;
+  CK(cudaMemcpyAsync(h->ndet.p, &nd, sizeof(nd), cudaMemcpyHostToDevice, h->stream), "set detection count");
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  h->n_frames = h->n_det_host; h->frames_done = true; h->have_info = true; h->planned = false; h->halo = n_halo;
+  return FMCW_OK;
+}
+
 fmcw_status fmcw_set_halo(fmcw_handle* h, const double* src, uint64_t count) {
   if (!h || (!src && count)) return FMCW_ERR_POINTER;
   BusyGuard g(h);

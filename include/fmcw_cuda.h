@@ -181,6 +181,12 @@ FMCW_API fmcw_status fmcw_stft(fmcw_handle* h, const float* x, uint64_t L, const
  *   fmcw_get_slow_time / fmcw_set_halo (neighbour exchange of window_length-1 samples) ->
  *   fmcw_stft_local_max -> all-reduce(max) -> fmcw_stft_sharded. */
 FMCW_API fmcw_status fmcw_get_slow_time(fmcw_handle* h, double* dst, uint64_t first, uint64_t count);
+/* Streaming (recordings whose frames or spectrogram do not fit the GPU, BASELINE configs[3]): the caller keeps the
+ * slow-time magnitudes (8 B per chirp of a detected frame) of the whole recording, collected chunk by chunk with
+ * fmcw_process_frames + fmcw_get_slow_time, and hands any piece of them back: x = L_local samples followed by n_halo
+ * (< window_length) samples that follow the piece.  L_local must be a multiple of num_chirps_per_frame.  The piece then
+ * behaves like a shard: fmcw_stft_local_max / fmcw_stft_sharded with the piece's global sample offset.  Host or device x. */
+FMCW_API fmcw_status fmcw_load_slow_time(fmcw_handle* h, const double* x, uint64_t L_local, uint64_t n_halo);
 FMCW_API fmcw_status fmcw_set_halo(fmcw_handle* h, const double* src, uint64_t count);
 FMCW_API fmcw_status fmcw_stft_local_max(fmcw_handle* h, uint64_t L_total, uint64_t sample_offset,
                                          double* pmax_raw_local);

@@ -328,3 +328,35 @@ def test_all_rx_streams_match_the_oracle_per_antenna():
             H.assert_spectrogram_contract(out["intensity"][:nc].T, ref["stft"]["intensity"])
     assert not np.array_equal(res_h[0]["intensity"][:100], res_h[1]["intensity"][:100])      # the antennas differ (phase offset)
     a.close()
+
+
+def test_streaming_recording_equals_one_shot():
+    """streaming.py (BASELINE configs[3] driver): frames pushed in chunks, the STFT in pieces through a small reusable
+    buffer -- the same result as one fmcw_run over the whole recording (spectrogram, track, nfft, max)."""
+    import torch
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    from fmcw_radar_processing_b200.streaming import StreamingRecording
+    case = H.make_case(n_frames=50, NTS=128, PN=64)
+    case["iq"][[7, 31]] = 2048
+    iq_d = torch.from_numpy(case["iq"]).cuda()
+    h0 = FmcwCuda(case["cfg"], case["calib"])
+    out0, inten0 = h0.run(iq_d)
+    info0 = h0.info()
+    ref = inten0[:info0["ncol_total"]].cpu().numpy()
+    s = StreamingRecording(case["cfg"], case["calib"])
+    s.reserve(50)
+    for f0 in range(0, 50, 12):
+        s.push_frames(iq_d[f0:f0 + 12].contiguous())
+    got = np.full_like(ref, np.nan)
+    buf = torch.empty((700 + 20, 1024), dtype=torch.float32, device="cuda")
+
+    def consumer(c0, n, b):
+        got[c0:c0 + n] = b[:n].cpu().numpy()
+
+    r = s.stft(buf, piece_cols=700, consumer=consumer)
+    assert r["L_total"] == info0["L_total"] and r["ncol_total"] == info0["ncol_total"] == r["ncol_local"] and r["pieces"] == 5
+    assert r["pmax_raw"] == pytest.approx(info0["pmax_raw"], rel=1e-6)
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref)) and np.nanmax(np.abs(got - ref)) <= 2e-4
+    rb = np.concatenate([t["range_bin"] for t in s.track])
+    assert np.array_equal(rb, out0["range_bin"].cpu().numpy())
+    s.close(); h0.close()
