@@ -297,7 +297,7 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   CK(pick(out ? out->doppler_row : nullptr, h->o_drow, nf * ND * 8, false, t), "alloc"); d.drow = (float2*)t;
   CK(pick(out ? out->slow_time_mag : nullptr, h->o_slow, nf * PN * 4, false, t), "alloc"); d.slow = (float*)t;
   CK(h->o_slow64.ensure(nf * PN * sizeof(sig_t)), "alloc slow-time rows");
-  CK(h->det_list.ensure(nf * 4), "alloc det_list");
+  CK(h->det_list.ensure(((nf + 1023) / 1024 * 33 + 8) * 4), "alloc compaction counts");
   CK(h->xc.ensure((nf * PN + c.window_length) * sizeof(sig_t)), "alloc slow-time signal");
   CK(h->colub.ensure((nf * PN + c.window_length) * 4), "alloc column bounds");
   h->st.col_ub = h->colub.as<float>();
@@ -318,8 +318,8 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   CK(cudaEventRecord(h->ev[0], h->stream), "event"); h->ev_valid[0] = true;
   CK(launch_frame_chain(p, h->stream), "frame chain kernel");
   CK(cudaEventRecord(h->ev[1], h->stream), "event"); h->ev_valid[1] = true;
-  CompactParams cp{d.det, n_frames, PN, h->o_slow64.as<sig_t>(), h->xc.as<sig_t>(), h->det_list.as<uint32_t>(),
-                   h->ndet.as<unsigned long long>()};
+  CompactParams cp{d.det, n_frames, PN, h->o_slow64.as<sig_t>(), h->xc.as<sig_t>(), nullptr,
+                   h->ndet.as<unsigned long long>(), h->det_list.as<uint32_t>()};
   CK(launch_compact(cp, h->stream), "compaction kernels");
   CK(cudaEventRecord(h->ev[2], h->stream), "event"); h->ev_valid[2] = true;
   h->n_frames = n_frames; h->frames_done = true; h->have_info = false; h->planned = false; h->halo = 0;

@@ -58,6 +58,7 @@ struct CompactParams {
   sig_t* xc;                  // compacted magnitudes
   uint32_t* det_list;         // [n_frames] frame index of the k-th detection
   unsigned long long* n_det;  // device scalar
+  uint32_t* counts;           // [ceil(n/1024) * 33] scratch of the two-launch form (long recordings), may be null
 };
 cudaError_t launch_compact(const CompactParams& p, cudaStream_t st);
 

@@ -119,15 +119,17 @@ struct WarpSmem {                                // byte offsets inside the dyna
 __host__ __device__ inline WarpSmem warp_smem_layout(uint32_t PN, int WF_WARPS) {
   WarpSmem L;
   int o = 0;
-  L.tw = o;   o += 15 * 16 * (int)sizeof(float4);          // (c, c, s, s) of W256^(s*k1), k1 = 1..15
-  L.wg = o;   o += NR * (int)sizeof(float2);               // (gw, gw)
-  L.wh = o;   o += NR * (int)sizeof(float4);               // (h_re, h_re, h_im, h_im)
+  // scalars, splat into both halves of a packed operand by the instruction itself (FFMA2 R, R.F32, ...): the LSU data pipe is
+  // this kernel's busiest unit (profiles/ncu_chain_r2.txt), so no table carries duplicated values
+  L.tw = o;   o += 15 * 16 * (int)sizeof(float2);          // (c, s) of W256^(s*k1), k1 = 1..15
+  L.wg = o;   o += NR * (int)sizeof(float);                // gw
+  L.wh = o;   o += NR * (int)sizeof(float2);               // (h_re, h_im)
   L.dtw = o;  o += MAX_ND * (int)sizeof(float2);
   L.dwin = o; o += MAX_ND * (int)sizeof(float);
   L.per_warp0 = o;
   int w = 0;
-  L.xch = w;  w += 2 * WF_XHALF * (int)sizeof(float4);     // 8,704 B; pass 2: G[256] double2 + X[PN] double2
-  const int need2 = NR * 16 + (int)PN * 16;
+  L.xch = w;  w += 2 * WF_XHALF * (int)sizeof(float4);     // 8,704 B; pass 2: X[PN] double2
+  const int need2 = (int)PN * 16;
   if (w < need2) w = need2;
   L.rmax = w; w += (NR + 16) * (int)sizeof(float);         // 8 pad floats each side for the neighbour loads
   L.csum = w; w += (int)PN * (int)sizeof(float2);
@@ -143,9 +145,9 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t NTS = p.NTS, PN = p.PN, ND = p.ND;
   const WarpSmem L = warp_smem_layout(PN, WF_WARPS);
-  float4* s_tw = reinterpret_cast<float4*>(smem_raw + L.tw);
-  float2* s_wg = reinterpret_cast<float2*>(smem_raw + L.wg);
-  float4* s_wh = reinterpret_cast<float4*>(smem_raw + L.wh);
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw + L.tw);
+  float* s_wg = reinterpret_cast<float*>(smem_raw + L.wg);
+  float2* s_wh = reinterpret_cast<float2*>(smem_raw + L.wh);
   float2* s_dtw = reinterpret_cast<float2*>(smem_raw + L.dtw);
   float* s_dwin = reinterpret_cast<float*>(smem_raw + L.dwin);
 
@@ -155,13 +157,12 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
 
   // ---- read-only tables, once per CTA (the grid is persistent over frames) ----
   for (int i = tid; i < 15 * 16; i += WF_WARPS * 32) {
-    const float2 t = p.tw_pair[16 + i];
-    s_tw[i] = make_float4(t.x, t.x, t.y, t.y);
+    s_tw[i] = p.tw_pair[16 + i];
   }
   for (int i = tid; i < NR; i += WF_WARPS * 32) {
     const float4 w = (i < (int)p.nts_fft) ? p.win_tab[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s_wg[i] = make_float2(w.x, w.x);
-    s_wh[i] = make_float4(w.y, w.y, w.z, w.z);
+    s_wg[i] = w.x;
+    s_wh[i] = make_float2(w.y, w.z);
   }
   if (tid < (int)ND) s_dtw[tid] = p.dop_tw[tid];
   if (tid < MAX_ND) s_dwin[tid] = (tid < ndc) ? p.dop_win[tid] : 0.f;
@@ -173,8 +174,7 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
   float2* s_csum = reinterpret_cast<float2*>(wbase + L.csum);
   float2* s_row = reinterpret_cast<float2*>(wbase + L.row);
   float2* s_xw = s_row + MAX_ND;
-  double2* s_G = reinterpret_cast<double2*>(wbase + L.xch);
-  double2* s_X = s_G + NR;
+  double2* s_X = reinterpret_cast<double2*>(wbase + L.xch);
 
   if (lane < 8) { s_rmax[-8 + lane] = 0.f; s_rmax[NR + lane] = 0.f; }
   const float2 nts2 = make_float2((float)NTS, (float)NTS);
@@ -251,8 +251,10 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
 #pragma unroll
       for (int r = 0; r < 4 * NZ; ++r) {
         const int n = s + 16 * r;
-        const float2 wg = s_wg[n];
-        const float4 wh = s_wh[n];
+        const float g1 = s_wg[n];
+        const float2 h1 = s_wh[n];
+        const float2 wg = make_float2(g1, g1);
+        const float4 wh = make_float4(h1.x, h1.x, h1.y, h1.y);
         // (code - mean)*NTS is an exact integer (|.| < 2^24); one rounding in the windowing multiply-add
         const float2 dI = __ffma2_rn(nts2, fi[r], nsI), dQ = __ffma2_rn(nts2, fq[r], nsQ);
         v[r].re = __ffma2_rn(wg, dI, make_float2(-wh.x, -wh.y));
@@ -266,8 +268,8 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
       dft16<NZ>(v);
 #pragma unroll
       for (int k1 = 1; k1 < 16; ++k1) {
-        const float4 t = s_tw[(k1 - 1) * 16 + s];
-        const float2 c2 = make_float2(t.x, t.y), s2 = make_float2(t.z, t.w);
+        const float2 t = s_tw[(k1 - 1) * 16 + s];
+        const float2 c2 = make_float2(t.x, t.x), s2 = make_float2(t.y, t.y);
         const cx2 a = v[k1];
         v[k1].re = __ffma2_rn(a.im, neg2(s2), __fmul2_rn(a.re, c2));
         v[k1].im = __ffma2_rn(a.re, s2, __fmul2_rn(a.im, c2));
@@ -362,68 +364,98 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
     // pass 1),  H = FFT of the calibration term (tabulated per bin at create).  This row feeds the STFT, whose bins
     // sit 100+ dB under its DC term, so it is carried in float64.
     __syncwarp();                              // every lane is done with the transpose slices
-    for (int n = lane; n < (int)p.nts_fft; n += 32) {
-      const double gw = __ldg(p.win_tab_d + 3 * n);
-      const double2 tw = __ldg(p.tw_d + (((uint32_t)n * (uint32_t)kbin) & (NR - 1)));
-      s_G[n] = make_double2(gw * tw.x, gw * tw.y);
-    }
-    const double2 Hk = __ldg(p.hfft_d + kbin);
+    // 32 lanes per chirp, lane l owns samples l + 32 i: G stays in registers (2 NZ values), a chirp is four (NZ = 2) fully
+    // coalesced 128-byte loads, and eight chirps are reduced over the warp together (a halving butterfly: 36 shuffles per
+    // eight chirps).  The LSU data pipe is this kernel's busiest unit; this pass no longer touches shared memory in its loop.
+    constexpr int NG = 2 * NZ;
+    double2 G[NG];
     double2 Gs = make_double2(0.0, 0.0);       // sum_n G[n]
-    for (int n = lane; n < (int)p.nts_fft; n += 32) {
-      const double gw = __ldg(p.win_tab_d + 3 * n);
-      const double2 tw = __ldg(p.tw_d + (((uint32_t)n * (uint32_t)kbin) & (NR - 1)));
-      Gs.x += gw * tw.x;
-      Gs.y += gw * tw.y;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const int n = lane + 32 * i;
+      G[i] = make_double2(0.0, 0.0);
+      if (EXACT || n < (int)p.nts_fft) {
+        const double gw = __ldg(p.win_tab_d + 3 * n);
+        const double2 tw = __ldg(p.tw_d + (((uint32_t)n * (uint32_t)kbin) & (NR - 1)));
+        G[i] = make_double2(gw * tw.x, gw * tw.y);
+      }
+      Gs.x += G[i].x;
+      Gs.y += G[i].y;
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
       Gs.x += __shfl_xor_sync(0xffffffffu, Gs.x, m);
       Gs.y += __shfl_xor_sync(0xffffffffu, Gs.y, m);
     }
-    __syncwarp();
+    const double2 Hk = __ldg(p.hfft_d + kbin);
     {
-      const int grp = lane >> 3, j8 = lane & 7;            // eight lanes per chirp, four chirps per step
-      constexpr int NW2 = 8 * NZ;                          // words per lane and chirp (EXACT: nts_fft = 64 NZ)
-      uint32_t wcur[NW2], wnxt[NW2];
-      auto load_group = [&](uint32_t c0, uint32_t (&w)[NW2]) {
-        const uint32_t c = c0 + grp;
-        const bool live = c < PN;
-        const uint32_t* cbp = fbase + (uint64_t)(live ? c : 0) * NTS + j8;
+      constexpr bool PF2 = (NZ <= 2);          // NZ = 4: eight chirps x eight words already take 64 registers
+      uint32_t wcur[8][NG], wnxt[PF2 ? 8 : 1][PF2 ? NG : 1];
+      auto load_batch = [&](uint32_t c0, auto& w) {
 #pragma unroll
-        for (int i = 0; i < NW2; ++i) w[i] = (live && (EXACT || (uint32_t)(j8 + 8 * i) < p.nts_fft)) ? __ldg(cbp + 8 * i) : 0u;
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t c = c0 + j;
+          const bool live = EXACT || c < PN;
+          const uint32_t* cbp = fbase + (uint64_t)(live ? c : 0) * NTS + lane;
+#pragma unroll
+          for (int i = 0; i < NG; ++i)
+            w[j][i] = (live && (EXACT || (uint32_t)(lane + 32 * i) < p.nts_fft)) ? __ldg(cbp + 32 * i) : 0u;
+        }
       };
-      load_group(0, wcur);
-      for (uint32_t c0 = 0; c0 < PN; c0 += 4) {
-        const uint32_t c = c0 + grp;
-        const bool live = c < PN;
-        if (c0 + 4 < PN) load_group(c0 + 4, wnxt);         // the next four chirps are in flight during this step
-        double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+      const bool b16 = (lane & 16) != 0, b8 = (lane & 8) != 0, b4 = (lane & 4) != 0;
+      const uint32_t my_chirp = (b16 ? 4u : 0u) + (b8 ? 2u : 0u) + (b4 ? 1u : 0u);      // the chirp of the batch this lane ends up with
+      if (PF2) load_batch(0, wcur);
+      for (uint32_t c0 = 0; c0 < PN; c0 += 8) {
+        if (!PF2) load_batch(c0, wcur);
+        if constexpr (PF2) { if (c0 + 8 < PN) load_batch(c0 + 8, wnxt); }         // the next eight chirps are in flight during this step
+        double ar[8], ai[8];
 #pragma unroll
-        for (int i = 0; i < NW2; i += 2) {
-          const uint32_t w0 = wcur[i], w1 = wcur[i + 1];
-          const bool in0 = EXACT || (uint32_t)(j8 + 8 * i) < p.nts_fft, in1 = EXACT || (uint32_t)(j8 + 8 * i + 8) < p.nts_fft;
-          const double2 G0 = in0 ? s_G[j8 + 8 * i] : make_double2(0.0, 0.0);
-          const double2 G1 = in1 ? s_G[j8 + 8 * i + 8] : make_double2(0.0, 0.0);
-          const double cI0 = cvtd_lo(w0), cQ0 = cvtd_hi(w0), cI1 = cvtd_lo(w1), cQ1 = cvtd_hi(w1);
-          ar0 = fma(G0.x, cI0, fma(-G0.y, cQ0, ar0));
-          ai0 = fma(G0.x, cQ0, fma(G0.y, cI0, ai0));
-          ar1 = fma(G1.x, cI1, fma(-G1.y, cQ1, ar1));
-          ai1 = fma(G1.x, cQ1, fma(G1.y, cI1, ai1));
-        }
-        double ar = ar0 + ar1, ai = ai0 + ai1;
+        for (int j = 0; j < 8; ++j) {
+          double r0 = 0.0, i0 = 0.0;
 #pragma unroll
-        for (int m = 4; m >= 1; m >>= 1) {
-          ar += __shfl_xor_sync(0xffffffffu, ar, m);
-          ai += __shfl_xor_sync(0xffffffffu, ai, m);
+          for (int i = 0; i < NG; ++i) {
+            const double cI = cvtd_lo(wcur[j][i]), cQ = cvtd_hi(wcur[j][i]);
+            r0 = fma(G[i].x, cI, fma(-G[i].y, cQ, r0));
+            i0 = fma(G[i].x, cQ, fma(G[i].y, cI, i0));
+          }
+          ar[j] = r0; ai[j] = i0;
         }
-        if (live && j8 == 0) {
+        // halving butterfly: after xor 16 a lane keeps four chirps, after xor 8 two, after xor 4 one; then a plain reduction
+        double r4[4], i4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double keep_r = b16 ? ar[j + 4] : ar[j], send_r = b16 ? ar[j] : ar[j + 4];
+          const double keep_i = b16 ? ai[j + 4] : ai[j], send_i = b16 ? ai[j] : ai[j + 4];
+          r4[j] = keep_r + __shfl_xor_sync(0xffffffffu, send_r, 16);
+          i4[j] = keep_i + __shfl_xor_sync(0xffffffffu, send_i, 16);
+        }
+        double r2[2], i2[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double keep_r = b8 ? r4[j + 2] : r4[j], send_r = b8 ? r4[j] : r4[j + 2];
+          const double keep_i = b8 ? i4[j + 2] : i4[j], send_i = b8 ? i4[j] : i4[j + 2];
+          r2[j] = keep_r + __shfl_xor_sync(0xffffffffu, send_r, 8);
+          i2[j] = keep_i + __shfl_xor_sync(0xffffffffu, send_i, 8);
+        }
+        double ar1 = (b4 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? r2[0] : r2[1], 4);
+        double ai1 = (b4 ? i2[1] : i2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? i2[0] : i2[1], 4);
+        ar1 += __shfl_xor_sync(0xffffffffu, ar1, 2);
+        ai1 += __shfl_xor_sync(0xffffffffu, ai1, 2);
+        ar1 += __shfl_xor_sync(0xffffffffu, ar1, 1);
+        ai1 += __shfl_xor_sync(0xffffffffu, ai1, 1);
+        const uint32_t c = c0 + my_chirp;
+        if ((lane & 3) == 0 && c < PN) {
           // sum_n G[n] (NTS c[n] - sum c) = NTS * acc - (sum c) * Gsum: the codes enter as they are, the mean leaves here
           const float2 csf = s_csum[c];
           const double sI = (double)csf.x, sQ = (double)csf.y;
-          s_X[c] = make_double2((double)NTS * ar - (sI * Gs.x - sQ * Gs.y) - Hk.x, (double)NTS * ai - (sI * Gs.y + sQ * Gs.x) - Hk.y);
+          s_X[c] = make_double2((double)NTS * ar1 - (sI * Gs.x - sQ * Gs.y) - Hk.x, (double)NTS * ai1 - (sI * Gs.y + sQ * Gs.x) - Hk.y);
         }
+        if constexpr (PF2) {
 #pragma unroll
-        for (int i = 0; i < NW2; ++i) wcur[i] = wnxt[i];
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < NG; ++i) wcur[j][i] = wnxt[j][i];
+        }
       }
     }
     __syncwarp();

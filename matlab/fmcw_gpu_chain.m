@@ -4,7 +4,7 @@ function r = fmcw_gpu_chain(cmd, frame_i16, calib_data, c)
 %
 %   r = fmcw_gpu_chain('run', frame_i16, calib_data, c)
 %
-% frame_i16  int16 [2 x NTS x PN x RX x N] ADC codes as returned by the f_parse_data2 shim in this folder
+% frame_i16  int16 [2 x NTS x PN x RX x N] ADC codes as returned by f_parse_data2_raw.m in this folder
 % c          struct with the fmcw_configurations field names (radar_processing.m lines 645-672)
 %
 % r has the variables the rest of radar_processing.m uses, shaped exactly like the reference's:

@@ -32,7 +32,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
     n, PN, NTS, n_rx = args.frames, 64, 128, 3
-    sx, cfg, scene = build_workload(n)
+    sx, cfg, scene = build_workload("c2")
     calib = synth.default_calib(n_rx, NTS) / 4095.0
     h = FmcwCuda(cfg, calib, device=local_rank)
 
@@ -54,11 +54,11 @@ def main():
     info_nccl = h.info()
     track_nccl = res["track"].clone()
 
-    # peer-memory mailboxes, two passes (the second reuses the mailboxes)
+    # peer-memory mailboxes, four passes (reusing the mailboxes; the third captures the exchange as a CUDA graph, the fourth replays it)
     used = run.use_peer_mailbox()
     ok = True
     if used:
-        for _ in range(2):
+        for _ in range(4):
             inten_mb = torch.full((cap, 1024), -1.0, dtype=torch.float32, device=dev)
             res = run.step_async(iq, out, inten_mb)
             torch.cuda.synchronize(dev)
