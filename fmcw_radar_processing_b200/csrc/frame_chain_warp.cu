@@ -140,7 +140,7 @@ __host__ __device__ inline WarpSmem warp_smem_layout(uint32_t PN, int WF_WARPS) 
 }
 
 // EXACT: NTS == 64*NZ and PN % 4 == 0 and no range-spectrum export: no predicates anywhere in pass 1.
-template <int NZ, bool EXACT, int MINB, int WF_WARPS>
+template <int NZ, bool EXACT, int MINB, int WF_WARPS, int UNPK>
 __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(const ChainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t NTS = p.NTS, PN = p.PN, ND = p.ND;
@@ -220,8 +220,16 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
       float2 sI = make_float2(0.f, 0.f), sQ = make_float2(0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < 4 * NZ; ++r) {
-        fi[r] = make_float2(cvt_lo(wa[r]), cvt_lo(wb[r]));     // I2F.F32.S16 on the half-registers: no unpack instructions
-        fq[r] = make_float2(cvt_hi(wa[r]), cvt_hi(wb[r]));
+        if (UNPK == 0) {
+          fi[r] = make_float2(cvt_lo(wa[r]), cvt_lo(wb[r]));     // I2F.F32.S16 on the half-registers: no unpack instructions (XU pipe)
+          fq[r] = make_float2(cvt_hi(wa[r]), cvt_hi(wb[r]));
+        } else {
+          // ALU + FMA pipes instead: the sign-flipped code dropped into the mantissa of 2^23, one packed subtract removes the bias
+          const uint32_t ta = wa[r] ^ 0x80008000u, tb = wb[r] ^ 0x80008000u;
+          const float2 bias2 = make_float2(8421376.0f, 8421376.0f);       // 2^23 + 2^15
+          fi[r] = sub2(make_float2(__uint_as_float(__byte_perm(ta, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(tb, 0x4B000000u, 0x7610))), bias2);
+          fq[r] = sub2(make_float2(__uint_as_float(__byte_perm(ta, 0x4B000000u, 0x7632)), __uint_as_float(__byte_perm(tb, 0x4B000000u, 0x7632))), bias2);
+        }
         sI = add2(sI, fi[r]);
         sQ = add2(sQ, fq[r]);
       }
@@ -510,16 +518,16 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
   }
 }
 
-template <int NZ, bool EXACT, int MINB, int WF_WARPS = 4>
+template <int NZ, bool EXACT, int MINB, int WF_WARPS = 4, int UNPK = 0>
 cudaError_t launch_variant(const ChainParams& p, int sms, cudaStream_t st) {
   const WarpSmem L = warp_smem_layout(p.PN, WF_WARPS);
   const int per_sm = MINB;
   const uint64_t ctas_needed = (p.n_frames + WF_WARPS - 1) / WF_WARPS;
   const uint64_t max_grid = (uint64_t)sms * per_sm;
   const unsigned grid = (unsigned)(ctas_needed < max_grid ? ctas_needed : max_grid);
-  cudaError_t e = cudaFuncSetAttribute(frame_chain_warp_kernel<NZ, EXACT, MINB, WF_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  cudaError_t e = cudaFuncSetAttribute(frame_chain_warp_kernel<NZ, EXACT, MINB, WF_WARPS, UNPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return e;
-  frame_chain_warp_kernel<NZ, EXACT, MINB, WF_WARPS><<<grid, WF_WARPS * 32, L.total, st>>>(p);
+  frame_chain_warp_kernel<NZ, EXACT, MINB, WF_WARPS, UNPK><<<grid, WF_WARPS * 32, L.total, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -542,6 +550,8 @@ cudaError_t launch_frame_chain_warp(const ChainParams& p, cudaStream_t st) {
       return exact ? launch_variant<NZ_, true, (NZ_ == 4 ? 3 : 4)>(p, sms, st) : launch_variant<NZ_, false, (NZ_ == 4 ? 3 : 4)>(p, sms, st); \
     return exact ? launch_variant<NZ_, true, 3>(p, sms, st) : launch_variant<NZ_, false, 3>(p, sms, st);    \
   } while (0)
+  static const int unpk = env_int("FMCW_CHAIN_UNPACK", 0);
+  if (unpk == 1 && nz == 2 && exact) return launch_variant<2, true, 3, 4, 1>(p, sms, st);
   if (nz == 1) FMCW_WF(1);
   if (nz == 2) FMCW_WF(2);
   FMCW_WF(4);

@@ -27,6 +27,8 @@
 // chunk c-1 overlap the lg2 phase of chunk c.
 #include <cstdlib>
 
+#include <cuda.h>
+
 #include "fmcw_internal.cuh"
 
 namespace fmcw {
@@ -53,7 +55,12 @@ constexpr int TC_OFF_B = 2 * TC_A_BYTES;
 constexpr int TC_OFF_STG = TC_OFF_B + 2 * TC_B_BYTES;
 constexpr int TC_OFF_AQ = TC_OFF_STG + 2 * TC_SBUF * 4;
 constexpr int TC_OFF_BAR = TC_OFF_AQ + (MAX_NQ + 32) * 4;
-constexpr int TC_SMEM = TC_OFF_BAR + 24 * 8 + 16;
+constexpr int TC_SMEM = TC_OFF_BAR + 32 * 8 + 16;
+// TMA-store epilogue: per buffer and quarter two boxes of [32 columns][32 queries] floats in the 128-byte swizzle
+constexpr int TC_TBOX = 32 * 32 * 4;                   // 4 KB
+constexpr int TC_TQ = 2 * TC_TBOX;                     // per quarter
+constexpr int TC_TBUF = 4 * TC_TQ;                     // per buffer (32 KB; fits the 34.8 KB of the padded rows)
+static_assert(TC_OFF_STG % 1024 == 0 && (TC_SBUF * 4) >= TC_TBUF, "swizzled boxes need 1024-byte alignment");
 static_assert(MAX_NQ % TC_QC == 0, "query table is padded to whole chunks");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,6 +154,10 @@ __device__ __forceinline__ void stg64_if(float* p, float2 v, bool ok) {
 __device__ __forceinline__ void stg32_if(float* p, float v, bool ok) {
   asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q st.global.f32 [%0], %1;\n}" ::"l"(p), "f"(v), "r"((int)ok) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(smem), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ float2 lds64(uint32_t a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
@@ -222,21 +233,21 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
 //   LAYOUT 0: time-major out[col][query]; LAYOUT 1: frequency-major out[query][ld_cols].
 //   NQC: compile-time number of queries (1024) for the time-major fast path, 0 = run-time nq.
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT, int NQC>
+template <int LAYOUT, int NQC, bool TMA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
                unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, int dbg_mode,
-               const double* __restrict__ gmax_dev) {
+               const double* __restrict__ gmax_dev, const __grid_constant__ CUtensorMap tmap) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   float* sA = reinterpret_cast<float*>(smem);                          // 2 x (E | O)
   float* sB = reinterpret_cast<float*>(smem + TC_OFF_B);               // 2 x (C | S)
   float* s_stg = reinterpret_cast<float*>(smem + TC_OFF_STG);          // 2 x [4 quarters][32 columns][TC_SROW]
   float* s_aq = reinterpret_cast<float*>(smem + TC_OFF_AQ);            // [MAX_NQ] interp1 weights (zero padded)
   float* s_ws = s_aq + MAX_NQ;                                         // [32] normalised window
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 24);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 32);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long cb = P->col_begin, ce = P->col_end, off = P->sample_offset;
@@ -261,6 +272,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
       mbar_init(BAR(8 + i), 1); mbar_init(BAR(10 + i), TC_EW);
     }
     for (int i = 0; i < 8; ++i) mbar_init(BAR(12 + i), 4);
+    for (int i = 0; i < 8; ++i) mbar_init(BAR(20 + i), 1);      // [20 + 2*quarter + buffer] TMA store of the buffer has read it
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == TC_EW) {
@@ -292,12 +304,12 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
     bool pending = false;
     float2 pend_v = make_float2(0.f, 0.f);
     auto flush_begin = [&]() {      // the other three warps of the quarter have staged their queries; first row in flight
-      if (LAYOUT != 0) return;
+      if (LAYOUT != 0 || TMA) return;
       if (pending) mbar_wait(pend_bar, pend_par);
       pend_v = lds64(pend_addr);
     };
     auto flush_col = [&](int j) {   // store row j (loaded one step earlier), load row j + 1
-      if (LAYOUT != 0) return;
+      if (LAYOUT != 0 || TMA) return;
       const bool ok = j < pend_cols;
       if (NQC > 0) {
         stg64_if(pend_ptr + (size_t)j * NQC, pend_v, ok);
@@ -348,12 +360,41 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (lane == 0) mbar_arrive(BAR(10 + ts));         // (warp-collective loads are complete) TMEM stage back to the MMA warp
         if (skip_math) { if (reA[0] + imB[15] == 123.456f) out[0] = 1.f; continue; }
+        if (TMA && sw == 0 && pending) {
+          // the quarter's rows of the previous chunk are staged: hand them to the TMA engine (two swizzled boxes of 32 columns
+          // x 32 queries), then release the buffer of the chunk before it, whose store has finished reading by now
+          mbar_wait(pend_bar, pend_par);
+          if (lane == 0) {
+            tma_store_2d(&tmap, pend_addr, pend_q, pend_cols);
+            tma_store_2d(&tmap, pend_addr + TC_TBOX, pend_q + 32, pend_cols);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (cseq >= 2) mbar_arrive(BAR(20 + 2 * qd + ts));   // the store of chunk cseq - 2 has read this chunk's buffer: free again
+          }
+          __syncwarp();
+        }
         const uint32_t a_w = a_aq + (uint32_t)(ch * TC_QC * 4);
         float o[16];
         flush_begin();
         half_chunk(reA, imA, a_w, o, 0);
         half_chunk(reB, imB, a_w + 32u, o + 8, 4);
-        if (LAYOUT == 0) {
+        if (LAYOUT == 0 && TMA) {
+          // buffer ts was last used by chunk cseq - 2, whose store was released at the start of this chunk
+          if (cseq >= 2) mbar_wait(BAR(20 + 2 * qd + ts), (uint32_t)(((cseq >> 1) - 1) & 1));
+          const uint32_t box = smem_u32(s_stg) + (uint32_t)(ts * TC_TBUF + qd * TC_TQ + (sw >> 1) * TC_TBOX + lane * 128);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(box + (uint32_t)(((((sw & 1) * 4 + i) ^ (lane & 7))) << 4), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(12 + 2 * qd + ts));
+          pending = true;
+          pend_bar = BAR(12 + 2 * qd + ts);
+          pend_par = (uint32_t)((cseq >> 1) & 1);
+          pend_addr = smem_u32(s_stg) + (uint32_t)(ts * TC_TBUF + qd * TC_TQ);
+          pend_q = ch * TC_QC;                                                   // first query of the chunk
+          pend_cols = (int)(tile_col0 - cb) + qd * 32;                           // first column (row of the output) of the quarter
+        } else if (LAYOUT == 0) {
           const uint32_t aw = a_st_w + (uint32_t)(ts * TC_SBUF * 4);
 #pragma unroll
           for (int i = 0; i < 4; ++i) sts128(aw + (uint32_t)(i * 16), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
@@ -378,6 +419,16 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
     flush_begin();
 #pragma unroll
     for (int j = 0; j < 8; ++j) flush_col(j);
+    if (TMA && sw == 0 && pending) {
+      mbar_wait(pend_bar, pend_par);
+      if (lane == 0) {
+        tma_store_2d(&tmap, pend_addr, pend_q, pend_cols);
+        tma_store_2d(&tmap, pend_addr + TC_TBOX, pend_q + 32, pend_cols);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+      __syncwarp();
+    }
   } else if (warp == TC_EW) {
     // ===================== MMA issuer: one thread drives the tensor core =====================
     if (lane == 0) {
@@ -493,13 +544,36 @@ cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float
   return cudaGetLastError();
 }
 
-template <int L, int Q>
+// Tensor map of the spectrogram [capacity_cols][1024] floats for the TMA-store epilogue: boxes of 32 queries x 32 columns, 128-byte
+// swizzle.  cuTensorMapEncodeTiled comes through the runtime's driver entry point (no link against libcuda).
+static bool make_out_tmap(CUtensorMap* map, float* out, unsigned long long capacity_cols) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static const encode_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    cudaGetLastError();
+    return (encode_fn)p;
+  }();
+  if (!fn || capacity_cols == 0) return false;
+  const cuuint64_t dims[2] = {1024, capacity_cols};
+  const cuuint64_t strides[1] = {4096};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int L, int Q, bool TMA = false>
 static cudaError_t launch_tc(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, cudaStream_t st,
-                             const double* gmax_dev, int sms, int dbg) {
-  cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<L, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+                             const double* gmax_dev, int sms, int dbg, const CUtensorMap* map = nullptr) {
+  cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<L, Q, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   if (e != cudaSuccess) return e;
-  stft_tc_kernel<L, Q><<<sms, TC_THREADS, TC_SMEM, st>>>(t, g, x, out, tcB, capacity_cols, ld_cols, d_err, dbg, gmax_dev);
+  CUtensorMap dummy{};
+  const CUtensorMap& tm = map ? *map : dummy;
+  stft_tc_kernel<L, Q, TMA><<<sms, TC_THREADS, TC_SMEM, st>>>(t, g, x, out, tcB, capacity_cols, ld_cols, d_err, dbg, gmax_dev, tm);
   return cudaGetLastError();
 }
 
@@ -511,6 +585,13 @@ cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const si
 #define FMCW_TC_ARGS t, g, x, out, tcB, capacity_cols, ld_cols, d_err, st, gmax_dev, sms, dbg
   if (layout != 0) return launch_tc<1, 0>(FMCW_TC_ARGS);
   // the fast path stores 64-bit pairs: 1,024 queries and an 8-byte aligned spectrogram
+  static const int use_tma = env_int("FMCW_TC_TMA", 1);
+  if (use_tma && g.nq == 1024 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // TMA-store epilogue: the staged rows leave through the async proxy (no LDS / STG on the LSU pipe).  Rows between the
+    // column count and capacity_cols that share the last tile are overwritten (with copies of the last column).
+    CUtensorMap map;
+    if (make_out_tmap(&map, out, capacity_cols)) return launch_tc<0, 1024, true>(FMCW_TC_ARGS, &map);
+  }
   if (g.nq == 1024 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) return launch_tc<0, 1024>(FMCW_TC_ARGS);
   return launch_tc<0, 0>(FMCW_TC_ARGS);
 #undef FMCW_TC_ARGS
