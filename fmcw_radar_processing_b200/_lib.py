@@ -82,6 +82,7 @@ EXPORTS = {
                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmcw_stft_finegrid": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_uint32, C.c_void_p, C.c_uint64,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fmcw_range_doppler_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "fmcw_range_spectrum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "fmcw_json_append_f32": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int]),
     "fmcw_json_append_f64": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int]),

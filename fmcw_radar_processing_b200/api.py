@@ -297,6 +297,12 @@ class FmcwCuda:
         flat = out.reshape(-1)[:nc.value * nr.value] if isinstance(out, np.ndarray) else out.view(-1)[:nc.value * nr.value]
         return flat.reshape(nc.value, nr.value), F
 
+    def range_doppler_map(self, iq, frame: int) -> np.ndarray:
+        """Full range-Doppler map of one frame in dB, [range_fft_size][Doppler_fft_size] (RP:216-219 on every range row)."""
+        out = np.empty((self.NR, self.ND), dtype=np.float32)
+        self._check(self.lib.fmcw_range_doppler_map(self._h, _ptr(iq), int(iq.shape[0]), frame, out.ctypes.data))
+        return out
+
     def range_spectrum(self, iq, frame: int, chirp: int) -> np.ndarray:
         """abs(range_fft(:, chirp)) of one frame (RP:410-411), 0-based indices."""
         out = np.empty(self.NR, dtype=np.float32)

@@ -146,7 +146,7 @@ struct fmcw_handle {
   std::atomic_flag busy = ATOMIC_FLAG_INIT;
   std::string err;
   // chain tables
-  DevBuf win_tab, win_tab_d, tw_d, hfft_d, tw_pair, tw_re, tw_im, dop_tw, dop_win;
+  DevBuf win_tab, win_tab_d, tw_d, hfft_d, dop_win_d, tw_pair, tw_re, tw_im, dop_tw, dop_win;
   int bin_lo = 0, bin_hi = -1;
   // STFT tables
   StftTables st{};
@@ -554,7 +554,8 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   }
   const std::vector<double> wd = chebwin_sym((int)PN, 100.0);
   std::vector<float> dwin(ND, 0.f);
-  for (uint32_t i = 0; i < ND && i < PN; ++i) dwin[i] = (float)(2.0 * wd[i]);
+  std::vector<double> dwin_d(ND, 0.0);
+  for (uint32_t i = 0; i < ND && i < PN; ++i) { dwin[i] = (float)(2.0 * wd[i]); dwin_d[i] = 2.0 * wd[i]; }
   // range gate of f_search_peak: (n-1)*dist_per_bin in [min_distance, max_distance], n = 3..len-2
   h->bin_lo = NR; h->bin_hi = -1;
   for (int n = 3; n <= NR - 2; ++n) {
@@ -593,7 +594,7 @@ fmcw_status fmcw_create(const fmcw_config* cfg, const double* calib_data, uint64
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   ok(upload(h->win_tab, wt, h->stream)); ok(upload(h->tw_pair, twp, h->stream));
-  ok(upload(h->win_tab_d, wtd, h->stream)); ok(upload(h->tw_d, twd, h->stream)); ok(upload(h->hfft_d, hfft, h->stream));
+  ok(upload(h->win_tab_d, wtd, h->stream)); ok(upload(h->tw_d, twd, h->stream)); ok(upload(h->hfft_d, hfft, h->stream)); ok(upload(h->dop_win_d, dwin_d, h->stream));
   ok(upload(h->tw_re, twre, h->stream)); ok(upload(h->tw_im, twim, h->stream));
   ok(upload(h->dop_tw, dtw, h->stream)); ok(upload(h->dop_win, dwin, h->stream));
   ok(upload(h->swin, swin, h->stream)); ok(upload(h->swin_d, wk, h->stream));
@@ -628,7 +629,7 @@ void fmcw_destroy(fmcw_handle* h) {
   h->mb_step.release();
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->swin_d, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
-                   &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->hfft_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
+                   &h->o_rbin, &h->o_rmag, &h->o_dbin, &h->o_drow, &h->o_slow, &h->o_slow64, &h->f32_stage, &h->win_tab_d, &h->tw_d, &h->hfft_d, &h->dop_win_d, &h->xc, &h->det_list, &h->ndet, &h->inten,
                    &h->synth_tab, &h->tcb, &h->colub};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
@@ -1151,6 +1152,36 @@ fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_fr
   p.spec_out = d_spec; p.spec_frame = 0; p.spec_chirp = chirp;
   CK(launch_frame_chain(p, h->stream), "frame chain kernel");
   if (!dev) CK(cudaMemcpyAsync(out, d_spec, NR * 4, cudaMemcpyDeviceToHost, h->stream), "D2H spectrum");
+  CK(cudaStreamSynchronize(h->stream), "synchronize");
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_range_doppler_map(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, uint64_t frame, float* out_db) {
+  if (!h || !iq || !out_db) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  cudaSetDevice(h->device);
+  const fmcw_config& c = h->cfg;
+  if (frame >= n_frames) return fail(h, FMCW_ERR_SIZE, "frame out of range");
+  const size_t frame_words = (size_t)c.num_Rx_antennas * c.num_chirps_per_frame * c.num_ADC_samples_per_chirp;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(iq) + frame * frame_words;
+  if (!is_device_ptr(iq)) {
+    CK(h->iq_stage.ensure(frame_words * 4), "alloc iq staging");
+    CK(cudaMemcpyAsync(h->iq_stage.p, src, frame_words * 4, cudaMemcpyHostToDevice, h->stream), "H2D frame");
+    src = h->iq_stage.as<uint32_t>();
+  }
+  ChainParams p{};
+  p.iq = src; p.n_frames = 1; p.NTS = c.num_ADC_samples_per_chirp; p.PN = c.num_chirps_per_frame;
+  p.n_rx = c.num_Rx_antennas; p.rx_sel = c.rx_select; p.ND = c.Doppler_fft_size;
+  p.nts_fft = p.NTS < (uint32_t)NR ? p.NTS : (uint32_t)NR;
+  p.win_tab_d = h->win_tab_d.as<double>(); p.tw_d = h->tw_d.as<double2>(); p.hfft_d = h->hfft_d.as<double2>();
+  p.dop_win = h->dop_win.as<float>(); p.dop_win_d = h->dop_win_d.as<double>();
+  const size_t bytes = (size_t)NR * c.Doppler_fft_size * 4;
+  const bool dev = is_device_ptr(out_db);
+  float* d_out = out_db;
+  if (!dev) { CK(h->f32_stage.ensure(bytes), "alloc"); d_out = h->f32_stage.as<float>(); }
+  CK(launch_range_doppler_map(p, 0, d_out, h->stream), "range-Doppler map kernel");
+  if (!dev) CK(cudaMemcpyAsync(out_db, d_out, bytes, cudaMemcpyDeviceToHost, h->stream), "D2H map");
   CK(cudaStreamSynchronize(h->stream), "synchronize");
   return FMCW_OK;
 }

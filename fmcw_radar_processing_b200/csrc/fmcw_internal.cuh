@@ -31,6 +31,7 @@ struct ChainParams {
   const float*  tw_im;
   const float2* dop_tw;      // [ND] W_ND^k
   const float*  dop_win;     // [min(PN,ND)] first taps of 2*chebwin(PN) (RP:139, 219)
+  const double* dop_win_d;   // the same taps in float64 (range-Doppler map export)
   int32_t bin_lo, bin_hi;    // range gate, 0-based inclusive (RP:126-127 through f_search_peak)
   float range_thr, dop_thr;
   int32_t peak_mode;
@@ -50,6 +51,9 @@ int env_int(const char* name, int dflt);    // atoi(getenv(name)) or dflt
 // one warp per frame, two chirps per lane (frame_chain_warp.cu); launch_frame_chain dispatches to it when supported
 bool chain_warp_supported(const ChainParams& p);
 cudaError_t launch_frame_chain_warp(const ChainParams& p, cudaStream_t st);
+
+// full range-Doppler dB map of one frame (frame_chain.cu)
+cudaError_t launch_range_doppler_map(const ChainParams& p, uint64_t frame, float* out_db, cudaStream_t st);
 
 // ---- compaction of the detected frames' slow-time rows (RP:257-260) ------------------------------
 struct CompactParams {

@@ -406,6 +406,62 @@ __global__ void __launch_bounds__(NT, 768 / NT) frame_chain_kernel(const ChainPa
   }
 }
 
+// Full range-Doppler dB map of ONE frame (an export, not on the throughput path): one thread per range bin.  The range row
+// X_c[r] of every chirp by direct float64 DFT of the exact integer samples (the tables of the slow-time pass: G = gw * W^(n r),
+// H = FFT of the calibration term), then RP:217-219 per row and 20*log10(|.|).
+__global__ void __launch_bounds__(NR) range_doppler_map_kernel(const ChainParams p, uint64_t frame, float* __restrict__ out_db) {
+  extern __shared__ __align__(16) unsigned char rd_raw[];
+  int2* s_sum = reinterpret_cast<int2*>(rd_raw);                       // [PN] integer sums of every chirp (RP:204)
+  const int r = threadIdx.x;
+  const uint32_t NTS = p.NTS, PN = p.PN, ND = p.ND;
+  const int ndc = (int)min(PN, ND);
+  const uint32_t* fbase = p.iq + ((frame * p.n_rx + p.rx_sel) * (uint64_t)PN) * NTS;
+  for (uint32_t c = r; c < PN; c += NR) {
+    int sI = 0, sQ = 0;
+    for (uint32_t n = 0; n < NTS; ++n) { const uint32_t w = __ldg(fbase + (uint64_t)c * NTS + n); sI += (int)(short)(w & 0xffffu); sQ += (int)w >> 16; }
+    s_sum[c] = make_int2(sI, sQ);
+  }
+  __syncthreads();
+  const double2 H = p.hfft_d[r];
+  double mr = 0.0, mi = 0.0;
+  double xr[MAX_ND], xi[MAX_ND];
+  for (uint32_t c = 0; c < PN; ++c) {
+    const int2 cs = s_sum[c];
+    double ar = 0.0, ai = 0.0;
+    for (uint32_t n = 0; n < p.nts_fft; ++n) {
+      const uint32_t w = __ldg(fbase + (uint64_t)c * NTS + n);
+      const double gw = p.win_tab_d[3 * n];
+      const double2 tw = p.tw_d[(n * (uint32_t)r) & (NR - 1)];
+      const double dI = (double)((int)NTS * (int)(short)(w & 0xffffu) - cs.x), dQ = (double)((int)NTS * ((int)w >> 16) - cs.y);
+      const double gr = gw * tw.x, gi = gw * tw.y;
+      ar = fma(gr, dI, fma(-gi, dQ, ar));
+      ai = fma(gr, dQ, fma(gi, dI, ai));
+    }
+    ar -= H.x; ai -= H.y;
+    mr += ar; mi += ai;                                                 // mean over ALL chirps (RP:217)
+    if ((int)c < ndc) { xr[c] = ar; xi[c] = ai; }
+  }
+  mr /= (double)PN; mi /= (double)PN;
+  for (int i = 0; i < (int)ND; ++i) {
+    const int k = (i + (int)ND / 2) & ((int)ND - 1);                    // fftshift
+    double dr = 0.0, di = 0.0;
+    for (int c = 0; c < ndc; ++c) {
+      const double w = p.dop_win_d[c];
+      const double a = (xr[c] - mr) * w, b = (xi[c] - mi) * w;
+      double sn, cs;
+      sincospi(-2.0 * (double)((c * k) & ((int)ND - 1)) / (double)ND, &sn, &cs);
+      dr += a * cs - b * sn;
+      di += a * sn + b * cs;
+    }
+    out_db[r * ND + i] = (float)(10.0 * log10(dr * dr + di * di));      // 20*log10(|.|); -inf for an exact zero
+  }
+}
+
+cudaError_t launch_range_doppler_map(const ChainParams& p, uint64_t frame, float* out_db, cudaStream_t st) {
+  range_doppler_map_kernel<<<1, NR, (size_t)p.PN * sizeof(int2), st>>>(p, frame, out_db);
+  return cudaGetLastError();
+}
+
 template <int NZ, int NT>
 static cudaError_t launch_chain_variant(const ChainParams& p, int sms, cudaStream_t st) {
   const size_t smem = chain_smem_bytes_nw(p.PN, NT / 32);

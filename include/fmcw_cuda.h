@@ -240,6 +240,13 @@ FMCW_API fmcw_status fmcw_stft_finegrid(fmcw_handle* h, double f_lo_hz, double f
                                         uint64_t capacity_cols, uint64_t* first_bin, uint64_t* bin_step, uint64_t* n_rows,
                                         uint64_t* ncol);
 
+/* Full range-Doppler map of one frame in dB (north_star "|X| to dB"): RP:216-219 applied to EVERY range row instead of the
+ * detected one only -- per row: mean over chirps removed, 2*chebwin(PN) window, Doppler_fft_size-point FFT over the first
+ * min(PN, ND) chirps (fft(.,ND,2) truncates), fftshift -- then 20*log10(|.|).  The reference fills Rx_spectrum(:,:,1) with the
+ * target row only and never reads it (RP:221); this is the map its name promises.  out_db: [range_fft_size][Doppler_fft_size]
+ * floats (row-major), host or device. */
+FMCW_API fmcw_status fmcw_range_doppler_map(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, uint64_t frame, float* out_db);
+
 /* Range spectrum abs(range_fft(:, chirp)) of one frame (RP:410-411). out: [range_fft_size] floats. */
 FMCW_API fmcw_status fmcw_range_spectrum(fmcw_handle* h, const int16_t* iq, uint64_t n_frames,
                                          uint64_t frame, uint32_t chirp, float* out);

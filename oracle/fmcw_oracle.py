@@ -254,6 +254,17 @@ def process_frame(chirp, cal, cfg: Config) -> FrameOut:
     return FrameOut(stored, rmax, idx, mag, drow, didx, slow)
 
 
+def range_doppler_map_db(chirp, cal, cfg: Config):
+    """RP:216-219 applied to every range row of one frame (the reference fills the detected row only, RP:216-221), in dB:
+    20*log10(abs(fftshift(fft((X - mean(X,2)) .* (2*chebwin(PN)).', ND, 2), 2))), [NR x ND]."""
+    ND = cfg.Doppler_fft_size
+    rfft = fast_time(chirp[:, :, 0], cal, cfg)
+    rows = rfft - rfft.mean(axis=1, keepdims=True)
+    rd = sfft.fftshift(sfft.fft(rows * cfg.doppler_window_func[None, :], ND, axis=1), axes=1)
+    with np.errstate(divide="ignore"):
+        return 20 * np.log10(np.abs(rd))
+
+
 def speed_of(didx, cfg: Config):
     return (didx - cfg.Doppler_fft_size / 2 - 1) * -cfg.fD_per_bin * cfg.Hz_to_mps_constant   # RP:250
 

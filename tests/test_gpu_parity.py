@@ -360,3 +360,29 @@ def test_finegrid_psd_band_matches_literal(api):
     step = -(-rows.size // 16)
     assert small.shape[1] == -(-rows.size // step) and np.array_equal(small, psd[:, ::step]) and np.allclose(F2, F[::step])
     h.close()
+
+
+@pytest.mark.parametrize("NTS,PN,n_rx", [(128, 64, 1), (64, 16, 2), (256, 256, 1)])
+def test_full_range_doppler_map_db(api, NTS, PN, n_rx):
+    """fmcw_range_doppler_map: RP:216-219 on every range row of one frame, in dB (north_star "|X| to dB"); the row of the
+    detected bin is the Doppler row the chain itself reports."""
+    from oracle import fmcw_oracle as O
+    case = H.make_case(n_frames=3, NTS=NTS, PN=PN, n_rx=n_rx)
+    frames, n, calib, sx = O.f_parse_data2(case["iq"], case["calib_codes"], case["sxml"])
+    cal = O.calib_rx1(calib, case["ocfg"])
+    h = api(case["cfg"], case["calib"])
+    out = h.process_frames(case["iq"])
+    for f in (0, 2):
+        want = O.range_doppler_map_db(frames[f], cal, case["ocfg"])
+        got = h.range_doppler_map(case["iq"], f).astype(np.float64)
+        assert got.shape == want.shape == (256, 16)
+        peak = want.max()
+        strong = want > peak - 60
+        assert np.abs(got[strong] - want[strong]).max() < 1e-3
+        weak = np.isfinite(want) & ~strong
+        assert np.abs(10 ** ((got[weak] - want[weak]) / 20) - 1).max() < 1e-4        # float64 inside: 1e-4 relative everywhere
+        rb = int(out["range_bin"][f])
+        row = out["doppler_row"][f, :, 0] + 1j * out["doppler_row"][f, :, 1]
+        top = got[rb] > got[rb].max() - 40                      # the chain's own Doppler row is float32: compare its strong bins
+        assert np.abs(20 * np.log10(np.abs(row[top])) - got[rb][top]).max() < 2e-3
+    h.close()
