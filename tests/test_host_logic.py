@@ -127,3 +127,22 @@ def test_native_json_writer_matches_python_writer(tmp_path):
     assert np.array_equal(np.array(p["m64"]), d)            # the Python stand-in round-trips too
     gp = np.array([[np.nan if v is None else v for v in r] for r in p["intensity"]], dtype=np.float32)
     assert np.array_equal(gp[m], a[m])
+
+
+def test_spectrogram_png_writer(tmp_path):
+    """payloads.write_spectrogram_png (RP:332-348): jet, clim [-40 0], frequency upwards, decimated to max_width columns."""
+    import struct
+    import zlib
+    band = np.full((500, 40), -60.0, dtype=np.float32)         # [ncol][n_rows]
+    band[:, 0] = 0.0                                            # lowest frequency row at the maximum
+    band[:, 20] = -20.0
+    band[3, 5] = -np.inf
+    w, h = P.write_spectrogram_png(str(tmp_path / "s.png"), band, max_width=250)
+    assert (w, h) == (250, 40)
+    png = open(tmp_path / "s.png", "rb").read()
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    ilen = struct.unpack(">I", png[33:37])[0]
+    px = np.frombuffer(zlib.decompress(png[41:41 + ilen]), dtype=np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
+    assert tuple(px[-1, 0]) == (128, 0, 0)                      # 0 dB -> top of jet (dark red), bottom image row = lowest frequency
+    assert tuple(px[0, 0]) == (0, 0, 128)                       # below clim -> bottom of jet (dark blue)
+    assert px[h - 1 - 20, 0, 1] > 200                           # -20 dB = middle of the map: green channel saturated
