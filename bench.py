@@ -421,6 +421,11 @@ def main():
                                        "achieved": max(counts) * CHAIN_BYTES_PER_FRAME / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else None,
                                        "peak": peak, "unit": "GB/s", "note": "instruction-issue / FMA-pipe bound, not HBM bound (DESIGN.md 3.1)"},
                 "chain_gbs": chain_gbs, "chain_frac_of_peak": chain_gbs / peak}
+    # the write stream this kernel produces, issued alone by every SM (tests/cuda/tma_store_probe.cu, profiles/tma_store_probe_r2.txt)
+    WRITE_CEILING_GBS = 6060.0
+    if achieved:
+        roofline["write_ceiling"] = {"value": WRITE_CEILING_GBS, "unit": "GB/s", "frac": achieved / WRITE_CEILING_GBS,
+                                     "source": "profiles/tma_store_probe_r2.txt: the same 3-D box stores with idle SMs"}
     if roofline["frame_chain_kernel"]["achieved"]:
         roofline["frame_chain_kernel"]["frac"] = roofline["frame_chain_kernel"]["achieved"] / peak
     traffic_path = os.path.join(ROOT, "profiles", "stft_tc_traffic.json")

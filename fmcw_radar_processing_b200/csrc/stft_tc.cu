@@ -25,6 +25,7 @@
 // take 16 queries of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer, warp 18 A-tile builder.  TMEM (512 columns), the A
 // tiles, the B tiles and the output staging rows are double buffered: the MMAs of chunk c+1 and the stores of
 // chunk c-1 overlap the lg2 phase of chunk c.
+#include <cstdio>
 #include <cstdlib>
 
 #include <cuda.h>
@@ -40,7 +41,7 @@ constexpr int TC_HALF = 10;                            // folded taps
 constexpr int TC_M = 128, TC_N = 128, TC_K = 32;       // UMMA tile; K = 3 x 10 taps + 2 DC slots
 constexpr int TC_QC = TC_N / 2;                        // queries per chunk
 constexpr int TC_EW = 16;                              // epilogue warps
-constexpr int TC_THREADS = (TC_EW + 3) * 32;          // + MMA issuer, bulk-copy producer, A-tile builder
+constexpr int TC_THREADS = (TC_EW + 7) * 32;          // + MMA issuer, bulk-copy producer, A-tile builder, four TMA-store issuers
 constexpr int TC_A_MAT_BYTES = TC_M * TC_K * 4;        // 16 KB per A operand matrix (E or O)
 constexpr int TC_A_BYTES = 2 * TC_A_MAT_BYTES;
 constexpr int TC_B_MAT_BYTES = TC_N * TC_K * 4;        // 16 KB per B operand matrix (C or S)
@@ -90,6 +91,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(a), "r"(parity), "r"(1000000u) : "memory");
   }
+}
+// both barriers' try_waits are in flight together (one trip through the MIO queue instead of two)
+__device__ __forceinline__ void mbar_wait2(uint32_t a, uint32_t pa, uint32_t b, uint32_t pb) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p, q;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %5;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4, %5;\nand.pred p, p, q;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(pa), "r"(b), "r"(pb), "r"(1000000u) : "memory");
+  }
+}
+__device__ __forceinline__ bool mbar_test(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t a) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
@@ -157,6 +173,10 @@ __device__ __forceinline__ void stg32_if(float* p, float v, bool ok) {
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(tmap), "r"(smem), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tmap), "r"(smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ float2 lds64(uint32_t a) {
   float2 v;
@@ -233,11 +253,11 @@ __global__ void __launch_bounds__(256) stft_tc_prepare_kernel(StftTables t, Stft
 //   LAYOUT 0: time-major out[col][query]; LAYOUT 1: frequency-major out[query][ld_cols].
 //   NQC: compile-time number of queries (1024) for the time-major fast path, 0 = run-time nq.
 // ------------------------------------------------------------------------------------------------
-template <int LAYOUT, int NQC, bool TMA>
+template <int LAYOUT, int NQC, bool TMA, bool PROF = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __restrict__ out, const float* __restrict__ tcB,
                unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, int dbg_mode,
-               const double* __restrict__ gmax_dev, const __grid_constant__ CUtensorMap tmap) {
+               const double* __restrict__ gmax_dev, const __grid_constant__ CUtensorMap tmap, int tma3d) {
   StftPlan* P = t.plan;
   if (P->valid <= 0) { if (threadIdx.x == 0 && blockIdx.x == 0 && P->valid < 0) *d_err = P->valid; return; }
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -338,101 +358,128 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
         o[2 * j] = o2.x; o[2 * j + 1] = o2.y;
       }
     };
-    const bool skip_math = (dbg_mode == 1);
-    float reA[16], imA[16], reB[16], imB[16];              // accumulator halves: one in use, one in flight
+    const bool skip_math = (dbg_mode & 1);      // FMCW_TC_DEBUG bits (timing experiments, results are wrong): 1 no lg2 phase / stores,
+                                                // 2 A tiles built twice only, 8 no TMA stores
+    float reA[16], imA[16], reB[16], imB[16];              // accumulator halves
 
+    uint32_t pf[7] = {0, 0, 0, 0, 0, 0, 0}, pt = 0;       // PROF: cycles per phase of this warp (32-bit: short runs only)
+    auto tick = [&](int i) { if (PROF) { const uint32_t n = (uint32_t)clock(); pf[i] += n - pt; pt = n; } };
+    if (PROF) pt = (uint32_t)clock();
     unsigned long long it = 0;                            // local tile counter
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const unsigned long long tile_col0 = cb + tile * TC_M;
-      const unsigned long long warp_col0 = tile_col0 + (unsigned long long)(qd * 32 + sw * 8);   // first of the warp's 8 store columns
-      const int wcols = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 8ull ? (ce - warp_col0) : 8ull);
-      const bool col_ok = (tile_col0 + m) < ce;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
-        const int ts = (int)(cseq & 1);
-        const uint32_t c0 = t_lane + (uint32_t)(ts * 2 * TC_N);
-        mbar_wait(BAR(8 + ts), (uint32_t)((cseq >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tmem_ld32(c0, reA, reB);
-        tmem_ld32(c0 + TC_N, imA, imB);
-        tmem_wait_ld(reA, imA);
-        tmem_wait_ld(reB, imB);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (lane == 0) mbar_arrive(BAR(10 + ts));         // (warp-collective loads are complete) TMEM stage back to the MMA warp
-        if (skip_math) { if (reA[0] + imB[15] == 123.456f) out[0] = 1.f; continue; }
-        if (TMA && sw == 0 && pending) {
-          // the quarter's rows of the previous chunk are staged: hand them to the TMA engine (two swizzled boxes of 32 columns
-          // x 32 queries), then release the buffer of the chunk before it, whose store has finished reading by now
-          mbar_wait(pend_bar, pend_par);
-          if (lane == 0) {
-            tma_store_2d(&tmap, pend_addr, pend_q, pend_cols);
-            tma_store_2d(&tmap, pend_addr + TC_TBOX, pend_q + 32, pend_cols);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (cseq >= 2) mbar_arrive(BAR(20 + 2 * qd + ts));   // the store of chunk cseq - 2 has read this chunk's buffer: free again
+    if constexpr (TMA) {
+      // ---- fast path (time-major, 1,024 queries): the staged boxes leave through the TMA-store warp.  Per chunk a warp makes
+      // three trips through the MIO queue it shares with the MUFUs of its neighbours (barrier pair, TMEM load, staging stores);
+      // the chunk loop is unrolled by two so that the TMEM stage / staging buffer and every barrier address are immediates.
+      static_assert(LAYOUT == 0 && NQC > 0 && (NQC / TC_QC) % 4 == 0, "parities below assume a multiple of four chunks per tile");
+      constexpr int NCH = NQC / TC_QC;
+      uint32_t a_box[4];                                  // this lane's four 16-byte pieces of its staged row (128-byte swizzle)
+      {
+        const uint32_t box0 = smem_u32(s_stg) + (uint32_t)(qd * TC_TQ + (sw >> 1) * TC_TBOX + lane * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a_box[i] = box0 + (uint32_t)(((((sw & 1) * 4 + i) ^ (lane & 7))) << 4);
+      }
+      const uint32_t b_tfull = BAR(8), b_tempty = BAR(10), b_sfull = BAR(12 + 2 * qd), b_sfree = BAR(20 + 2 * qd);
+      if (dbg_mode >> 8) __nanosleep((unsigned)(sw * (dbg_mode >> 8) * 16));      // experiment: start the four warps of a quarter out of phase
+      for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        uint32_t a_w = a_aq;
+#pragma unroll 1
+        for (int ch2 = 0; ch2 < NCH; ch2 += 2) {
+          const uint32_t par = (uint32_t)((ch2 >> 1) & 1);   // (chunk sequence number >> 1) & 1: NCH / 2 is even
+#pragma unroll
+          for (int ts = 0; ts < 2; ++ts) {
+            tick(0);
+            mbar_wait(b_tfull + 8u * ts, par);          // accumulators of this chunk ready
+            tick(1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tmem_ld32(t_lane + (uint32_t)(ts * 2 * TC_N), reA, reB);
+            tmem_ld32(t_lane + (uint32_t)(ts * 2 * TC_N + TC_N), imA, imB);
+            tmem_wait_ld(reA, imA);
+            tmem_wait_ld(reB, imB);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive(b_tempty + 8u * ts);   // TMEM stage back to the MMA warp
+            tick(2);
+            if (skip_math) { if (reA[0] + imB[15] == 123.456f) out[0] = 1.f; continue; }
+            float o[16];
+            if ((dbg_mode & 64) && sw > ((dbg_mode >> 2) & 1)) {   // experiment: only one (64) or two (68) warps per quarter run the lg2 phase
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = reA[i] + imB[i];
+            } else {
+              half_chunk(reA, imA, a_w, o, 0);
+              half_chunk(reB, imB, a_w + 32u, o + 8, 4);
+            }
+            a_w += (uint32_t)(TC_QC * 4);
+            if (PROF) { asm volatile("" :: "f"(o[0]), "f"(o[3]), "f"(o[7]), "f"(o[11]), "f"(o[15])); }
+            tick(4);
+            if (it > 0 || ch2 > 0) mbar_wait(b_sfree + 8u * ts, par ^ 1u);   // staging buffer ts (last used two chunks ago) read by its store
+            tick(5);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              sts128(a_box[i] + (uint32_t)(ts * TC_TBUF), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_sfull + 8u * ts);    // (release) this warp's 16 queries of the quarter's box pair are staged
+            tick(6);
           }
-          __syncwarp();
-        }
-        const uint32_t a_w = a_aq + (uint32_t)(ch * TC_QC * 4);
-        float o[16];
-        flush_begin();
-        half_chunk(reA, imA, a_w, o, 0);
-        half_chunk(reB, imB, a_w + 32u, o + 8, 4);
-        if (LAYOUT == 0 && TMA) {
-          // buffer ts was last used by chunk cseq - 2, whose store was released at the start of this chunk
-          if (cseq >= 2) mbar_wait(BAR(20 + 2 * qd + ts), (uint32_t)(((cseq >> 1) - 1) & 1));
-          const uint32_t box = smem_u32(s_stg) + (uint32_t)(ts * TC_TBUF + qd * TC_TQ + (sw >> 1) * TC_TBOX + lane * 128);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            sts128(box + (uint32_t)(((((sw & 1) * 4 + i) ^ (lane & 7))) << 4), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(12 + 2 * qd + ts));
-          pending = true;
-          pend_bar = BAR(12 + 2 * qd + ts);
-          pend_par = (uint32_t)((cseq >> 1) & 1);
-          pend_addr = smem_u32(s_stg) + (uint32_t)(ts * TC_TBUF + qd * TC_TQ);
-          pend_q = ch * TC_QC;                                                   // first query of the chunk
-          pend_cols = (int)(tile_col0 - cb) + qd * 32;                           // first column (row of the output) of the quarter
-        } else if (LAYOUT == 0) {
-          const uint32_t aw = a_st_w + (uint32_t)(ts * TC_SBUF * 4);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sts128(aw + (uint32_t)(i * 16), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(12 + 2 * qd + ts));  // this warp's 16 queries of the quarter's 32 x 64 outputs are staged
-          pending = true;
-          pend_bar = BAR(12 + 2 * qd + ts);
-          pend_par = (uint32_t)((cseq >> 1) & 1);
-          pend_addr = a_st_r + (uint32_t)(ts * TC_SBUF * 4);
-          pend_q = ch * TC_QC + 2 * lane;
-          pend_ptr = out + (warp_col0 - cb) * (unsigned long long)nq + pend_q;
-          pend_cols = wcols;
-        } else if (col_ok) {
-          // frequency-major: lanes = consecutive columns, coalesced 128-byte rows straight from registers
-          float* p = out + (unsigned long long)(ch * TC_QC + sw * 16) * ld_cols + (tile_col0 + m - cb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (NQC > 0 || ch * TC_QC + sw * 16 + i < nq) p[(unsigned long long)i * ld_cols] = o[i];
         }
       }
-    }
-    flush_begin();
+      if (PROF && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+        printf("PROF cta %3d warp %2d (quarter %d sub %d) chunks %llu | cycles per chunk: loop %5u  t_full %5u  ld %5u  math %5u  free %5u  sts %5u\n",
+               blockIdx.x, warp, qd, sw, it * NCH, pf[0] / (uint32_t)(it * NCH), pf[1] / (uint32_t)(it * NCH), pf[2] / (uint32_t)(it * NCH),
+               pf[4] / (uint32_t)(it * NCH), pf[5] / (uint32_t)(it * NCH), pf[6] / (uint32_t)(it * NCH));
+    } else {
+      for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const unsigned long long tile_col0 = cb + tile * TC_M;
+        const unsigned long long warp_col0 = tile_col0 + (unsigned long long)(qd * 32 + sw * 8);   // first of the warp's 8 store columns
+        const int wcols = (warp_col0 >= ce) ? 0 : (int)((ce - warp_col0) < 8ull ? (ce - warp_col0) : 8ull);
+        const bool col_ok = (tile_col0 + m) < ce;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
+          const int ts = (int)(cseq & 1);
+          const uint32_t c0 = t_lane + (uint32_t)(ts * 2 * TC_N);
+          mbar_wait(BAR(8 + ts), (uint32_t)((cseq >> 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          tmem_ld32(c0, reA, reB);
+          tmem_ld32(c0 + TC_N, imA, imB);
+          tmem_wait_ld(reA, imA);
+          tmem_wait_ld(reB, imB);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) mbar_arrive(BAR(10 + ts));         // (warp-collective loads are complete) TMEM stage back to the MMA warp
+          if (skip_math) { if (reA[0] + imB[15] == 123.456f) out[0] = 1.f; continue; }
+          const uint32_t a_w = a_aq + (uint32_t)(ch * TC_QC * 4);
+          float o[16];
+          flush_begin();
+          half_chunk(reA, imA, a_w, o, 0);
+          half_chunk(reB, imB, a_w + 32u, o + 8, 4);
+          if (LAYOUT == 0) {
+            const uint32_t aw = a_st_w + (uint32_t)(ts * TC_SBUF * 4);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) flush_col(j);
-    if (TMA && sw == 0 && pending) {
-      mbar_wait(pend_bar, pend_par);
-      if (lane == 0) {
-        tma_store_2d(&tmap, pend_addr, pend_q, pend_cols);
-        tma_store_2d(&tmap, pend_addr + TC_TBOX, pend_q + 32, pend_cols);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            for (int i = 0; i < 4; ++i) sts128(aw + (uint32_t)(i * 16), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(12 + 2 * qd + ts));  // this warp's 16 queries of the quarter's 32 x 64 outputs are staged
+            pending = true;
+            pend_bar = BAR(12 + 2 * qd + ts);
+            pend_par = (uint32_t)((cseq >> 1) & 1);
+            pend_addr = a_st_r + (uint32_t)(ts * TC_SBUF * 4);
+            pend_q = ch * TC_QC + 2 * lane;
+            pend_ptr = out + (warp_col0 - cb) * (unsigned long long)nq + pend_q;
+            pend_cols = wcols;
+          } else if (col_ok) {
+            // frequency-major: lanes = consecutive columns, coalesced 128-byte rows straight from registers
+            float* p = out + (unsigned long long)(ch * TC_QC + sw * 16) * ld_cols + (tile_col0 + m - cb);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (NQC > 0 || ch * TC_QC + sw * 16 + i < nq) p[(unsigned long long)i * ld_cols] = o[i];
+          }
+        }
       }
-      __syncwarp();
+      flush_begin();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) flush_col(j);
     }
   } else if (warp == TC_EW) {
     // ===================== MMA issuer: one thread drives the tensor core =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      long long mw_b = 0, mw_t = 0, mw_m = 0;         // PROF: cycles waiting for B tiles / for the TMEM stage / issuing (or executing, bit 32)
       unsigned long long it = 0;
       for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int abuf = (int)(it & 1);
@@ -442,8 +489,12 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
           const int st = (int)(cseq & 1);
           const uint32_t par = (uint32_t)((cseq >> 1) & 1);
+          long long q0 = 0, q1 = 0, q2 = 0;
+          if (PROF) q0 = clock64();
           mbar_wait(BAR(4 + st), par);               // B tile landed
+          if (PROF) q1 = clock64();
           mbar_wait(BAR(10 + st), par ^ 1);          // TMEM stage drained (passes immediately the first two times)
+          if (PROF) { q2 = clock64(); mw_b += q1 - q0; mw_t += q2 - q1; }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t aB = smem_u32(sB) + (uint32_t)(st * TC_B_BYTES);
 #pragma unroll
@@ -456,9 +507,16 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           }
           umma_commit(BAR(6 + st));                    // B stage consumed
           umma_commit(BAR(8 + st));                    // accumulators ready
+          if (PROF) {                                   // timing only: the issuer waits for its own MMAs (serialises the pipeline!)
+            if (dbg_mode & 32) { mbar_wait(BAR(8 + st), par); mw_m += clock64() - q2; }
+            else mw_m += clock64() - q2;
+          }
         }
         umma_commit(BAR(2 + abuf));                    // A buffer consumed
       }
+      if (PROF && (blockIdx.x == 0 || blockIdx.x == 77) && it > 0)
+        printf("PROF cta %3d MMA issuer | cycles per chunk: wait B %5lld  wait TMEM stage %5lld  issue%s %5lld\n", blockIdx.x,
+               mw_b / (long long)(it * n_chunks), mw_t / (long long)(it * n_chunks), (dbg_mode & 32) ? " + execute" : "", mw_m / (long long)(it * n_chunks));
     }
     __syncwarp();
   } else if (warp == TC_EW + 2) {
@@ -471,7 +529,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
       const int buf = (int)(it & 1);
       mbar_wait(BAR(2 + buf), (uint32_t)(((it >> 1) & 1) ^ 1));   // the MMAs of the tile that last used this buffer retired
 #pragma unroll 1
-      for (int r = 0; r < TC_M / 32; ++r) {
+      for (int r = 0; r < ((dbg_mode & 2) && it >= 2 ? 0 : TC_M / 32); ++r) {
         const int m = r * 32 + lane;                       // row of the tile = spectrogram column = TMEM lane
         unsigned long long col = cb + tile * TC_M + m;
         if (col >= ce) col = ce - 1;
@@ -511,6 +569,56 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(0 + buf));
     }
+  } else if (warp >= TC_EW + 3) {
+    // ===================== TMA-store issuer (fast path only) =====================
+    // Four warps (one thread each), one per quarter: wait until the quarter's four warps have staged their box pair (32 columns x 64
+    // queries, two 128-byte-swizzled boxes, one 3-D tensor store), fence (the proxy fence sits here, after the acquire of the barrier
+    // the writers released, so the epilogue warps neither fence nor wait for a store), store, and hand the buffer back (free barrier)
+    // as soon as the store has read it.
+    if constexpr (TMA) {
+      if (lane == 0 && !(dbg_mode & 1)) {
+        constexpr uint32_t NCH = NQC / TC_QC;
+        const uint32_t n_local = (n_tiles > blockIdx.x) ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+        const int q = warp - (TC_EW + 3);
+        const uint32_t b_sfull = BAR(12 + 2 * q), b_sfree = BAR(20 + 2 * q);
+        const uint32_t src0 = smem_u32(s_stg) + (uint32_t)(q * TC_TQ);
+        long long sp[4] = {0, 0, 0, 0}, s0 = 0;        // PROF: wait staged / fence / store + commit / wait_group.read
+        const long long s_begin = PROF ? clock64() : 0;
+        for (uint32_t itl = 0; itl < n_local; ++itl) {
+          const int col = (int)((blockIdx.x + ((dbg_mode & 128) ? 0u : itl) * gridDim.x) * (uint32_t)TC_M) + q * 32;   // first output row of the quarter (experiment 128: every tile lands on the CTA's first, in L2)
+#pragma unroll 1
+          for (uint32_t ch = 0; ch < NCH; ++ch) {
+            const uint32_t ts = ch & 1u;
+            if (PROF) s0 = clock64();
+            mbar_wait(b_sfull + 8u * ts, (ch >> 1) & 1u);
+            if (PROF) { const long long n = clock64(); sp[0] += n - s0; s0 = n; }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads
+            if (PROF) { const long long n = clock64(); sp[1] += n - s0; s0 = n; }
+            const uint32_t src = src0 + ts * (uint32_t)TC_TBUF;
+            if (!(dbg_mode & 8)) {
+              if (tma3d) {
+                tma_store_3d(&tmap, src, 0, col, (int)(2u * ch));
+              } else {
+                tma_store_2d(&tmap, src, (int)(ch * TC_QC), col);
+                tma_store_2d(&tmap, src + TC_TBOX, (int)(ch * TC_QC) + 32, col);
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              if (PROF) { const long long n = clock64(); sp[2] += n - s0; s0 = n; }
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              if (PROF) { const long long n = clock64(); sp[3] += n - s0; s0 = n; }
+            }
+            mbar_arrive(b_sfree + 8u * ts);
+          }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (PROF && (blockIdx.x == 0 || blockIdx.x == 77) && n_local > 0) {
+          const long long tot = (long long)n_local * NCH;
+          printf("PROF cta %3d store issuer lane %d | cycles per chunk: wait staged %5lld  fence %5lld  store + commit %5lld  wait_group.read %5lld  all %5lld\n",
+                 blockIdx.x, q, sp[0] / tot, sp[1] / tot, sp[2] / tot, sp[3] / tot, (clock64() - s_begin) / tot);
+        }
+      }
+      __syncwarp();
+    }
   } else {
     // ===================== producer: B tiles by 1-D bulk copy =====================
     if (lane == 0) {
@@ -520,6 +628,7 @@ stft_tc_kernel(StftTables t, StftGeom g, const sig_t* __restrict__ x, float* __r
           const unsigned long long cseq = it * (unsigned long long)n_chunks + ch;
           const int st = (int)(cseq & 1);
           mbar_wait(BAR(6 + st), (uint32_t)(((cseq >> 1) & 1) ^ 1));
+          if ((dbg_mode & 16) && cseq >= 2) { mbar_arrive(BAR(4 + st)); continue; }     // timing experiment: B tiles never reloaded
           mbar_expect_tx(BAR(4 + st), TC_B_BYTES);
           bulk_g2s(smem_u32(sB) + (uint32_t)(st * TC_B_BYTES), tcB + (size_t)ch * (TC_B_BYTES / 4), TC_B_BYTES, BAR(4 + st));
         }
@@ -546,7 +655,7 @@ cudaError_t launch_stft_tc_prepare(const StftTables& t, const StftGeom& g, float
 
 // Tensor map of the spectrogram [capacity_cols][1024] floats for the TMA-store epilogue: boxes of 32 queries x 32 columns, 128-byte
 // swizzle.  cuTensorMapEncodeTiled comes through the runtime's driver entry point (no link against libcuda).
-static bool make_out_tmap(CUtensorMap* map, float* out, unsigned long long capacity_cols) {
+static bool make_out_tmap(CUtensorMap* map, float* out, unsigned long long capacity_cols, bool three_d) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -558,6 +667,15 @@ static bool make_out_tmap(CUtensorMap* map, float* out, unsigned long long capac
     return (encode_fn)p;
   }();
   if (!fn || capacity_cols == 0) return false;
+  if (three_d) {
+    // [query group of 32][column][32 queries]: one box = both 32-query halves of a chunk for 32 columns, laid out in shared memory
+    // half-major -- exactly the two 2-D boxes back to back
+    const cuuint64_t dims[3] = {32, capacity_cols, 32};
+    const cuuint64_t strides[2] = {4096, 128};
+    const cuuint32_t box[3] = {32, 32, 2}, estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   const cuuint64_t dims[2] = {1024, capacity_cols};
   const cuuint64_t strides[1] = {4096};
   const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
@@ -565,15 +683,15 @@ static bool make_out_tmap(CUtensorMap* map, float* out, unsigned long long capac
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int L, int Q, bool TMA = false>
+template <int L, int Q, bool TMA = false, bool PROF = false>
 static cudaError_t launch_tc(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
                              unsigned long long capacity_cols, unsigned long long ld_cols, int* d_err, cudaStream_t st,
-                             const double* gmax_dev, int sms, int dbg, const CUtensorMap* map = nullptr) {
-  cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<L, Q, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+                             const double* gmax_dev, int sms, int dbg, const CUtensorMap* map = nullptr, int tma3d = 0) {
+  cudaError_t e = cudaFuncSetAttribute(stft_tc_kernel<L, Q, TMA, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   if (e != cudaSuccess) return e;
   CUtensorMap dummy{};
   const CUtensorMap& tm = map ? *map : dummy;
-  stft_tc_kernel<L, Q, TMA><<<sms, TC_THREADS, TC_SMEM, st>>>(t, g, x, out, tcB, capacity_cols, ld_cols, d_err, dbg, gmax_dev, tm);
+  stft_tc_kernel<L, Q, TMA, PROF><<<sms, TC_THREADS, TC_SMEM, st>>>(t, g, x, out, tcB, capacity_cols, ld_cols, d_err, dbg, gmax_dev, tm, tma3d);
   return cudaGetLastError();
 }
 
@@ -590,7 +708,17 @@ cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const si
     // TMA-store epilogue: the staged rows leave through the async proxy (no LDS / STG on the LSU pipe).  Rows between the
     // column count and capacity_cols that share the last tile are overwritten (with copies of the last column).
     CUtensorMap map;
-    if (make_out_tmap(&map, out, capacity_cols)) return launch_tc<0, 1024, true>(FMCW_TC_ARGS, &map);
+    static const int want3d = env_int("FMCW_TC_TMA3D", 1);
+    int tma3d = want3d && make_out_tmap(&map, out, capacity_cols, true);
+    if (tma3d || make_out_tmap(&map, out, capacity_cols, false)) {
+      static const int prof = env_int("FMCW_TC_PROF", 0);       // per-warp phase timing printed by CTAs 0 and 77 (diagnostics)
+      if (prof) {
+        static bool told = false;
+        if (!told) { told = true; fprintf(stderr, "stft_tc: TMA store epilogue, %s boxes\n", tma3d ? "3-D" : "2-D"); }
+        return launch_tc<0, 1024, true, true>(FMCW_TC_ARGS, &map, tma3d);
+      }
+      return launch_tc<0, 1024, true>(FMCW_TC_ARGS, &map, tma3d);
+    }
   }
   if (g.nq == 1024 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) return launch_tc<0, 1024>(FMCW_TC_ARGS);
   return launch_tc<0, 0>(FMCW_TC_ARGS);
