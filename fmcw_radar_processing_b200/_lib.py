@@ -15,6 +15,8 @@ PEAK_STRONGEST, PEAK_FIRST = 0, 1
 LAYOUT_TIME_MAJOR, LAYOUT_FREQ_MAJOR = 0, 1
 OPT_ASYNC_HOST = 1
 OPT_STFT_PRECISION = 2      # 0: tensor-core TF32 x 2 kernel (default), 1: float64 kernel
+OPT_STFT_TILES_PER_CTA = 4  # n > 1: one CTA per n column tiles in the tensor-core STFT kernel (fleets of small recordings)
+OPT_RUN_GRAPH = 3           # 1: whole fmcw_run calls on device buffers are recorded and replayed as one CUDA graph
 
 
 class FmcwError(RuntimeError):
@@ -50,6 +52,10 @@ class fmcw_run_info(C.Structure):
                [("n_dtft_bins", C.c_uint32), ("n_refined", C.c_uint32), ("pmax_raw", C.c_double)]
 
 
+class fmcw_device_info(C.Structure):
+    _fields_ = [("info", fmcw_run_info), ("status", C.c_int32), ("reserved0", C.c_int32)]
+
+
 EXPORTS = {
     "fmcw_version": (C.c_char_p, []),
     "fmcw_status_string": (C.c_char_p, [C.c_int]),
@@ -60,6 +66,7 @@ EXPORTS = {
     "fmcw_synchronize": (C.c_int, [C.c_void_p]),
     "fmcw_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "fmcw_get_info": (C.c_int, [C.c_void_p, C.POINTER(fmcw_run_info)]),
+    "fmcw_set_info_target": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fmcw_get_timings": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4)]),
     "fmcw_process_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(fmcw_frame_out)]),
     "fmcw_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(fmcw_frame_out), C.POINTER(fmcw_stft_out)]),

@@ -85,6 +85,22 @@ class FmcwCuda:
         self._check(self.lib.fmcw_get_info(self._h, C.byref(inf)))
         return {n: getattr(inf, n) for n, _ in _lib.fmcw_run_info._fields_}
 
+    def set_info_target(self, device_ptr: int | None):
+        """Every later ``run`` ends by writing an ``fmcw_device_info`` (the ``info()`` scalars + a status word) to this
+        device address, stream-ordered; ``None`` disables.  ``parse_device_infos`` decodes a host copy."""
+        self._check(self.lib.fmcw_set_info_target(self._h, C.c_void_p(device_ptr or 0)))
+
+    @staticmethod
+    def parse_device_infos(raw: np.ndarray) -> list:
+        """``raw``: uint8 host array holding consecutive ``fmcw_device_info`` structs -> list of (info dict, status)."""
+        sz = C.sizeof(_lib.fmcw_device_info)
+        out = []
+        buf = np.ascontiguousarray(raw, dtype=np.uint8).tobytes()
+        for i in range(len(buf) // sz):
+            d = _lib.fmcw_device_info.from_buffer_copy(buf, i * sz)
+            out.append(({n: getattr(d.info, n) for n, _ in _lib.fmcw_run_info._fields_}, int(d.status)))
+        return out
+
     def timings(self) -> dict:
         """Device ms of the stages of the last run (CUDA events on the handle's stream)."""
         ms = (C.c_float * 4)()

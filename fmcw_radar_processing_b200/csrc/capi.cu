@@ -16,11 +16,15 @@ using namespace fmcw;
 
 namespace {
 
+// bumped by every (re)allocation of a scratch buffer: recorded run graphs hold the old addresses and are dropped
+std::atomic<unsigned long long> g_alloc_epoch{0};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, bytes);
@@ -166,6 +170,14 @@ struct fmcw_handle {
   bool async_host = false;   // FMCW_OPT_ASYNC_HOST: calls with (pinned) host buffers return after enqueueing
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, chain, compact, plan+max, main
   bool ev_valid[5] = {false, false, false, false, false};
+  // FMCW_OPT_RUN_GRAPH: a whole fmcw_run as one CUDA graph per set of (device) buffers.  A fleet of small recordings is bound by the
+  // GPU's launch rate (about 12 launches per recording), not by its work.
+  struct RunKey { const void* iq; uint64_t n; const void* fo[7]; const void* inten; uint64_t cap, ld; uint32_t layout; int precise;
+                  const void* info_dst; };
+  struct RunGraph { RunKey key; cudaGraphExec_t exec; int seen; unsigned long long epoch; };
+  std::vector<RunGraph> run_graphs;
+  bool run_graph_opt = false, capturing = false;
+  fmcw_device_info* info_dst = nullptr;
 };
 
 namespace {
@@ -315,13 +327,14 @@ fmcw_status run_frames(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, con
   p.doppler_bin = d.dbin; p.doppler_row = d.drow; p.slow_mag = d.slow; p.slow64 = h->o_slow64.as<sig_t>();
   p.spec_out = nullptr;
   for (bool& v : h->ev_valid) v = false;
-  CK(cudaEventRecord(h->ev[0], h->stream), "event"); h->ev_valid[0] = true;
+  const bool timed = !h->capturing;                   // (events recorded into a graph cannot be read back)
+  if (timed) { CK(cudaEventRecord(h->ev[0], h->stream), "event"); h->ev_valid[0] = true; }
   CK(launch_frame_chain(p, h->stream), "frame chain kernel");
-  CK(cudaEventRecord(h->ev[1], h->stream), "event"); h->ev_valid[1] = true;
+  if (timed) { CK(cudaEventRecord(h->ev[1], h->stream), "event"); h->ev_valid[1] = true; }
   CompactParams cp{d.det, n_frames, PN, h->o_slow64.as<sig_t>(), h->xc.as<sig_t>(), nullptr,
                    h->ndet.as<unsigned long long>(), h->det_list.as<uint32_t>()};
   CK(launch_compact(cp, h->stream), "compaction kernels");
-  CK(cudaEventRecord(h->ev[2], h->stream), "event"); h->ev_valid[2] = true;
+  if (timed) { CK(cudaEventRecord(h->ev[2], h->stream), "event"); h->ev_valid[2] = true; }
   h->n_frames = n_frames; h->frames_done = true; h->have_info = false; h->planned = false; h->halo = 0;
   return FMCW_OK;
 }
@@ -385,9 +398,11 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
     int spec_mode = 0;
     CK(join_lookahead(h, spec_mode), "join look-ahead plan");
     static const int use_graph = env_int("FMCW_GRAPH", 1) != 0;
-    const bool graphable = use_graph && from_device_count && compute_max && spec_mode == 2 && ++h->mx_eligible_calls > 1;
+    bool graphable = use_graph && from_device_count && compute_max && spec_mode == 2 && ++h->mx_eligible_calls > 1;
+    const bool mx_stale = !h->mx_exec || memcmp(&h->mx_key_tables, &h->st, sizeof(StftTables)) != 0 || h->mx_key_xc != h->xc.p;
+    if (h->capturing) graphable = false;                   // inside the recording of a whole run: plain launches join the outer graph
     if (graphable) {
-      if (!h->mx_exec || memcmp(&h->mx_key_tables, &h->st, sizeof(StftTables)) != 0 || h->mx_key_xc != h->xc.p) {
+      if (mx_stale) {
         if (h->mx_exec) { cudaGraphExecDestroy(h->mx_exec); h->mx_exec = nullptr; }
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
@@ -411,10 +426,10 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
     h->planned = true; h->plan_L = L_total; h->plan_off = offset; h->plan_avail = L_avail;
   }
   if (!compute_max) CK(launch_stft_set_max(h->st, pmax_override, h->stream), "stft set max");
-  CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true;
+  if (!h->capturing) { CK(cudaEventRecord(h->ev[3], h->stream), "event"); h->ev_valid[3] = true; }
   CK(launch_stft_main(h->st, h->geom, h->xc.as<sig_t>(), d_out, cap, d_ld, (int)sout->layout, h->derr.as<int>(), h->stream,
                       nullptr, h->stft_precise), "stft main kernel");
-  CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true;
+  if (!h->capturing) { CK(cudaEventRecord(h->ev[4], h->stream), "event"); h->ev_valid[4] = true; }
   h->have_info = false;
   if (!dev_out && h->async_host) {
     // no host round trip: copy the upper bound of the column count (columns past the real count are unspecified)
@@ -440,6 +455,50 @@ fmcw_status run_stft(fmcw_handle* h, bool from_device_count, uint64_t L_total, u
            "D2H intensity");
     }
     CK(cudaStreamSynchronize(h->stream), "synchronize");
+  }
+  return FMCW_OK;
+}
+
+// fmcw_set_info_target: the scalars of the run, on the device (the same fields fmcw_get_info derives on the host)
+__global__ void info_snapshot_kernel(const StftPlan* __restrict__ P, const unsigned long long* __restrict__ ndet,
+                                     const int* __restrict__ derr, uint64_t n_frames, uint32_t PN, fmcw_device_info* dst) {
+  fmcw_device_info d;
+  memset(&d, 0, sizeof(d));
+  d.info.n_frames = n_frames;
+  d.info.n_detected = *ndet;
+  d.info.L_local = *ndet * PN;
+  d.info.L_total = P->L_total; d.info.sample_offset = P->sample_offset; d.info.nfft = P->nfft;
+  d.info.ncol_total = P->ncol_total;
+  if (P->valid > 0) { d.info.col_begin = P->col_begin; d.info.ncol_local = P->col_end - P->col_begin; }
+  d.info.n_dtft_bins = (uint32_t)P->nb; d.info.n_refined = P->n_refined;
+  d.info.pmax_raw = P->pmax_raw;
+  d.status = *derr != 0 ? *derr : (P->valid < 0 ? P->valid : 0);
+  *dst = d;
+}
+
+// the body of fmcw_run: look-ahead plan, frames, compaction, STFT (and the info snapshot); no synchronisation with device buffers
+fmcw_status run_body(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const fmcw_frame_out* fout, const fmcw_stft_out* sout,
+                     bool& any_host) {
+  FrameDev d{};
+  const uint64_t L_spec = n_frames * h->cfg.num_chirps_per_frame;
+  if (L_spec >= h->cfg.window_length) {
+    // look-ahead: plan the STFT for "every frame detects a target" on a side stream while the frame chain runs;
+    // the real plan launch confirms it on the device (or plans again if the detection count differs)
+    fmcw_status fs = fork_lookahead(h, L_spec, 0, L_spec, L_spec);
+    if (fs != FMCW_OK) return fs;
+  }
+  fmcw_status s = run_frames(h, iq, n_frames, fout, d, any_host);
+  if (s != FMCW_OK) return s;
+  s = copy_frame_outputs(h, n_frames, fout, d);
+  if (s != FMCW_OK) return s;
+  const uint64_t L_up = n_frames * h->cfg.num_chirps_per_frame;
+  const uint64_t cols_up = L_up >= h->cfg.window_length ? (L_up - h->cfg.overlap) / h->geom.hop : 0;
+  s = run_stft(h, true, 0, 0, 0, 0, true, 0.0, sout, cols_up);
+  if (s != FMCW_OK) return s;
+  if (h->info_dst) {
+    info_snapshot_kernel<<<1, 1, 0, h->stream>>>(h->plan.as<StftPlan>(), h->ndet.as<unsigned long long>(), h->derr.as<int>(), n_frames,
+                                                 h->cfg.num_chirps_per_frame, h->info_dst);
+    CK(cudaGetLastError(), "info snapshot kernel");
   }
   return FMCW_OK;
 }
@@ -626,6 +685,8 @@ void fmcw_destroy(fmcw_handle* h) {
   if (h->side) cudaStreamSynchronize(h->side);
   if (h->mx_exec) { cudaGraphExecDestroy(h->mx_exec); h->mx_exec = nullptr; }
   if (h->mbx_exec) { cudaGraphExecDestroy(h->mbx_exec); h->mbx_exec = nullptr; }
+  for (auto& e : h->run_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+  h->run_graphs.clear();
   h->mb_step.release();
   DevBuf* all[] = {&h->win_tab, &h->tw_pair, &h->tw_re, &h->tw_im, &h->dop_tw, &h->dop_win, &h->plan, &h->bins, &h->kcb, &h->wdc,
                    &h->qpos, &h->aq, &h->qend, &h->coef, &h->swin, &h->swin_d, &h->hard, &h->derr, &h->gmax, &h->iq_stage, &h->o_rmax, &h->o_det,
@@ -718,6 +779,12 @@ fmcw_status fmcw_set_option(fmcw_handle* h, int option, int64_t value) {
     case FMCW_OPT_STFT_PRECISION:
       if (value != 0 && value != 1) return fail(h, FMCW_ERR_CONFIG, "FMCW_OPT_STFT_PRECISION takes 0 (fast) or 1 (float64)");
       h->stft_precise = (int)value; return FMCW_OK;
+    case FMCW_OPT_RUN_GRAPH: h->run_graph_opt = value != 0; return FMCW_OK;
+    case FMCW_OPT_STFT_TILES_PER_CTA:
+      if (value < 0 || value > 4096) return fail(h, FMCW_ERR_CONFIG, "FMCW_OPT_STFT_TILES_PER_CTA takes 0 .. 4096");
+      h->geom.tiles_per_cta = (uint32_t)value;
+      g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);     // recorded run graphs carry the old grid
+      return FMCW_OK;
     default: return fail(h, FMCW_ERR_CONFIG, "unknown option");
   }
 }
@@ -728,28 +795,84 @@ fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const
   BusyGuard g(h);
   if (!g.ok) return FMCW_ERR_BUSY;
   cudaSetDevice(h->device);
-  FrameDev d{};
   bool any_host = false;
-  const uint64_t L_spec = n_frames * h->cfg.num_chirps_per_frame;
-  if (L_spec >= h->cfg.window_length) {
-    // look-ahead: plan the STFT for "every frame detects a target" on a side stream while the frame chain runs;
-    // the real plan launch confirms it on the device (or plans again if the detection count differs)
-    fmcw_status fs = fork_lookahead(h, L_spec, 0, L_spec, L_spec);
-    if (fs != FMCW_OK) return fs;
+  // FMCW_OPT_RUN_GRAPH: the whole run as one graph per set of device buffers (first two sightings run plainly: they size the
+  // scratch buffers and build the inner plan + max graph; the third is recorded; later ones replay)
+  fmcw_handle::RunGraph* rg = nullptr;
+  if (h->run_graph_opt && n_frames && sout && sout->intensity && is_device_ptr(iq) && is_device_ptr(sout->intensity)) {
+    fmcw_handle::RunKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.iq = iq; key.n = n_frames;
+    const void* fo[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (fout) {
+      fo[0] = fout->range_max_abs; fo[1] = fout->detected; fo[2] = fout->range_bin; fo[3] = fout->range_mag;
+      fo[4] = fout->doppler_bin; fo[5] = fout->doppler_row; fo[6] = fout->slow_time_mag;
+    }
+    bool all_dev = true;
+    for (int i = 0; i < 7; ++i) { key.fo[i] = fo[i]; if (fo[i] && !is_device_ptr(fo[i])) all_dev = false; }
+    key.inten = sout->intensity; key.cap = sout->capacity_cols; key.ld = sout->ld_cols; key.layout = sout->layout;
+    key.precise = h->stft_precise; key.info_dst = h->info_dst;
+    if (all_dev) {
+      for (auto& e : h->run_graphs)
+        if (std::memcmp(&e.key, &key, sizeof(key)) == 0) { rg = &e; break; }
+      if (!rg && h->run_graphs.size() < 4096) {
+        h->run_graphs.push_back(fmcw_handle::RunGraph{key, nullptr, 0, 0});
+        rg = &h->run_graphs.back();
+      }
+    }
   }
-  fmcw_status s = run_frames(h, iq, n_frames, fout, d, any_host);
-  if (s != FMCW_OK) return s;
-  s = copy_frame_outputs(h, n_frames, fout, d);
-  if (s != FMCW_OK) return s;
-  const uint64_t L_up = n_frames * h->cfg.num_chirps_per_frame;
-  const uint64_t cols_up = L_up >= h->cfg.window_length ? (L_up - h->cfg.overlap) / h->geom.hop : 0;
-  s = run_stft(h, true, 0, 0, 0, 0, true, 0.0, sout, cols_up);
+  if (rg && rg->exec && rg->epoch != g_alloc_epoch.load(std::memory_order_relaxed)) {
+    cudaGraphExecDestroy(rg->exec);              // a scratch buffer moved since the recording
+    rg->exec = nullptr; rg->seen = 0;
+  }
+  if (rg && rg->exec) {
+    CK(cudaGraphLaunch(rg->exec, h->stream), "launch run graph");
+    for (bool& v : h->ev_valid) v = false;
+    h->n_frames = n_frames; h->frames_done = true; h->have_info = false; h->planned = true; h->halo = 0; h->lookahead = false;
+    h->plan_L = 0; h->plan_off = 0; h->plan_avail = 0;
+    return FMCW_OK;
+  }
+  const bool capture = rg && ++rg->seen >= 3 && !h->lookahead;
+  if (capture) {
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal), "begin capture");
+    h->capturing = true;
+  }
+  fmcw_status s = run_body(h, iq, n_frames, fout, sout, any_host);
+  if (capture) {
+    h->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (s != FMCW_OK || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      rg->seen = -1000000;                       // this buffer set is not recorded again
+      h->lookahead = false; h->frames_done = false; h->planned = false;
+      if (s != FMCW_OK) return s;
+      return cuda_fail(h, e, "end capture of the run");
+    }
+    const cudaError_t e2 = cudaGraphInstantiate(&rg->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { rg->exec = nullptr; rg->seen = -1000000; return cuda_fail(h, e2, "instantiate run graph"); }
+    rg->epoch = g_alloc_epoch.load(std::memory_order_relaxed);
+    CK(cudaGraphLaunch(rg->exec, h->stream), "launch run graph");
+    for (bool& v : h->ev_valid) v = false;
+    return FMCW_OK;
+  }
   if (s != FMCW_OK) return s;
   if (any_host && !h->async_host) {
     CK(cudaStreamSynchronize(h->stream), "synchronize");
     if (!h->have_info) { s = read_info(h); if (s != FMCW_OK) return s; }
     if (h->plan_host.valid == 0) return fail(h, FMCW_ERR_NO_DATA, "fewer than window_length slow-time samples");
   }
+  return FMCW_OK;
+}
+
+fmcw_status fmcw_set_info_target(fmcw_handle* h, fmcw_device_info* device_dst) {
+  if (!h) return FMCW_ERR_POINTER;
+  BusyGuard g(h);
+  if (!g.ok) return FMCW_ERR_BUSY;
+  if (device_dst && !is_device_ptr(device_dst)) return fail(h, FMCW_ERR_POINTER, "the info target must be device memory");
+  h->info_dst = device_dst;
   return FMCW_OK;
 }
 

@@ -100,6 +100,7 @@ struct StftGeom {
   uint32_t win, hop, nq;
   double fs;
   float rho;   // rigorous bound of max_{w >= pi/(win-1)} |W(w)| / W(0) of the STFT window (host, float64)
+  uint32_t tiles_per_cta;   // FMCW_OPT_STFT_TILES_PER_CTA (0 / 1: one CTA per SM): grid of the persistent STFT kernel for small recordings
 };
 
 

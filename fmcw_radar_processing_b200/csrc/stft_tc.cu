@@ -698,8 +698,16 @@ static cudaError_t launch_tc(const StftTables& t, const StftGeom& g, const sig_t
 cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const sig_t* x, float* out, const float* tcB,
                                 unsigned long long capacity_cols, unsigned long long ld_cols,
                                 int layout, int* d_err, cudaStream_t st, const double* gmax_dev) {
-  const int sms = device_sm_count();
+  int sms = device_sm_count();
   static const int dbg = env_int("FMCW_TC_DEBUG", 0);
+  // small recordings (a fleet of radars, each on its own stream): a CTA per FMCW_TC_TILES_PER_CTA tiles of the buffer's capacity
+  // instead of one per SM, so that the kernels of several recordings run side by side
+  static const int tiles_env = env_int("FMCW_TC_TILES_PER_CTA", 0);
+  const int tiles_per_cta = tiles_env > 0 ? tiles_env : (int)g.tiles_per_cta;
+  if (tiles_per_cta > 1) {
+    const unsigned long long want = (capacity_cols / TC_M + (unsigned long long)tiles_per_cta) / (unsigned long long)tiles_per_cta;
+    if (want < (unsigned long long)sms) sms = (int)(want < 1 ? 1 : want);
+  }
 #define FMCW_TC_ARGS t, g, x, out, tcB, capacity_cols, ld_cols, d_err, st, gmax_dev, sms, dbg
   if (layout != 0) return launch_tc<1, 0>(FMCW_TC_ARGS);
   // the fast path stores 64-bit pairs: 1,024 queries and an 8-byte aligned spectrogram

@@ -4,10 +4,18 @@
 A small recording (C1 shape: 500 frames) cannot fill a B200: its frame-chain grid is below one resident set and the
 plan / max kernels are launch bound.  ``Fleet`` keeps a pool of handles -- each with its own stream, tables and
 scratch -- deals the recordings round-robin and leaves every hand-off on the device, so the kernels of different
-radars overlap wherever the SMs have room.  The reference has no counterpart (one recording per MATLAB call).
+radars overlap wherever the SMs have room.  A pass is bound by the GPU's launch rate, not by its work (about 12 launches
+per recording, ~50 us apiece however many streams carry them), so every handle records each recording's whole run as one
+CUDA graph (``FMCW_OPT_RUN_GRAPH``) and the per-recording scalars stay on the device (``fmcw_set_info_target``) until one
+copy at the end of the pass.  The reference has no counterpart (one recording per MATLAB call).
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
 from .api import FmcwCuda
 
 
@@ -18,6 +26,11 @@ class Fleet:
         self.handles = [FmcwCuda(cfg, calib, device=device, torch_stream_sync=False) for _ in range(max(1, n_handles))]
         self._streams = [torch.cuda.ExternalStream(h.stream, device=self.device) for h in self.handles]
         self._bufs = {}                                # radar index -> (n_frames, outputs, intensity), reused by every pass
+        self._info_size = C.sizeof(_lib.fmcw_device_info)
+        self._infos = None                             # device bytes: one fmcw_device_info per recording
+        for h in self.handles:
+            h.set_option(_lib.OPT_RUN_GRAPH, 1)
+            h.set_option(_lib.OPT_STFT_TILES_PER_CTA, 8)
 
     def close(self):
         for h in self.handles:
@@ -29,7 +42,7 @@ class Fleet:
         current torch stream).  Returns one dict per radar: the per-frame outputs, ``intensity`` (device tensor whose
         first ``ncol`` rows are valid) and the run ``info``.  The result buffers belong to the fleet and are reused by
         the next pass (no allocation, hence no implicit device synchronisation, in the steady state).  Everything is
-        enqueued first; a handle is synchronised only when its slot is needed again or at the end."""
+        enqueued without a host round trip; the scalars of all recordings come back in one copy at the end."""
         import torch
         cur = torch.cuda.current_stream(self.device)
         h0 = self.handles[0]
@@ -41,30 +54,29 @@ class Fleet:
                 shape = (cols, h0.nq) if layout == 0 else (h0.nq, cols)
                 self._bufs[i] = (n, h0.alloc_frame_out(n, device=self.device),
                                  torch.empty(shape, dtype=torch.float32, device=self.device), layout)
+        nrec = len(recordings)
+        if self._infos is None or self._infos.numel() < nrec * self._info_size:
+            self._infos = torch.zeros(nrec * self._info_size, dtype=torch.uint8, device=self.device)
         for s in self._streams:
             s.wait_stream(cur)                       # inputs are ready
         nh = len(self.handles)
-        results = [None] * len(recordings)
-        pending = [None] * nh                        # per handle: (radar index, outputs, intensity)
-
-        def collect(slot):
-            idx, out, inten = pending[slot]
-            info = self.handles[slot].info()         # synchronises this handle's stream
-            results[idx] = dict(out, intensity=inten, info=info, ncol=info["ncol_local"])
-            pending[slot] = None
-
+        base = self._infos.data_ptr()
         for i, iq in enumerate(recordings):
-            slot = i % nh
-            if pending[slot] is not None:
-                collect(slot)
+            h = self.handles[i % nh]
             _, out, inten, _ = self._bufs[i]
-            self.handles[slot].run(iq, out, inten, layout=layout)
-            pending[slot] = (i, out, inten)
-        for slot in range(nh):
-            if pending[slot] is not None:
-                collect(slot)
+            h.set_info_target(base + i * self._info_size)
+            h.run(iq, out, inten, layout=layout)
         for s in self._streams:
             cur.wait_stream(s)
+        raw = self._infos[:nrec * self._info_size].cpu().numpy()       # waits for every handle (current stream)
+        results = []
+        for i, (info, status) in enumerate(FmcwCuda.parse_device_infos(raw)):
+            if status != 0:
+                raise RuntimeError(f"recording {i}: device-side failure {status} (see fmcw_device_info in include/fmcw_cuda.h)")
+            _, out, inten, _ = self._bufs[i]
+            results.append(dict(out, intensity=inten, info=info, ncol=info["ncol_local"]))
+        for h in self.handles:
+            h.set_info_target(None)
         return results
 
 

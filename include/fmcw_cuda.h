@@ -150,10 +150,31 @@ FMCW_API fmcw_status fmcw_synchronize(fmcw_handle* h);
  *      -260 dB when the slow-time signal is a level plus noise).
  *   1: float64 CUDA-core kernel, any window: 1e-4 relative at every finite level (measured 5e-6); about 13x the time of
  *      the default kernel (3.4 ms instead of 0.27 ms per 5,000-frame recording on a B200).
- * tests/helpers.py::assert_spectrogram_contract asserts exactly these bounds. */
-enum { FMCW_OPT_ASYNC_HOST = 1, FMCW_OPT_STFT_PRECISION = 2 };
+ * tests/helpers.py::assert_spectrogram_contract asserts exactly these bounds.
+ *
+ * FMCW_OPT_RUN_GRAPH = 3: 1 = fmcw_run calls whose buffers are all device memory are recorded as ONE CUDA graph per set of
+ *   buffers (input, outputs, info target) the third time the set is seen and replayed from then on.  For fleets of small
+ *   recordings (BASELINE C5): a 500-frame recording is about 12 kernel launches and the GPU's launch rate, not its work, bounds
+ *   the pass.  Results are identical; fmcw_get_timings reports 0 for replayed runs.
+ *
+ * FMCW_OPT_STFT_TILES_PER_CTA = 4: n > 1 = the persistent tensor-core STFT kernel is launched with one CTA per n tiles (128 columns)
+ *   of the output buffer's capacity instead of one per SM when that is fewer: the kernels of several small recordings on
+ *   different handles then run side by side (a fleet), at the price of one recording's own latency.  0 / 1 (default): one per SM. */
+enum { FMCW_OPT_ASYNC_HOST = 1, FMCW_OPT_STFT_PRECISION = 2, FMCW_OPT_RUN_GRAPH = 3, FMCW_OPT_STFT_TILES_PER_CTA = 4 };
 FMCW_API fmcw_status fmcw_set_option(fmcw_handle* h, int option, int64_t value);
 FMCW_API fmcw_status fmcw_get_info(fmcw_handle* h, fmcw_run_info* info);   /* synchronises */
+
+/* The scalars of a run without a host round trip: while a target is set, every fmcw_run on the handle ends by writing this
+ * struct to `device_dst` (device memory, stream-ordered after the run's kernels).  A fleet driver gives every recording its own
+ * slot and reads all of them with one copy after the pass.  status: 0, or the device-side failure code (-2 more DTFT bins than
+ * the plan tables hold, -3 chunk too large, -4 capacity_cols too small, -5 too many columns for the exhaustive max search).
+ * NULL disables. */
+typedef struct fmcw_device_info {
+  fmcw_run_info info;
+  int32_t status;
+  int32_t reserved0;
+} fmcw_device_info;
+FMCW_API fmcw_status fmcw_set_info_target(fmcw_handle* h, fmcw_device_info* device_dst);
 
 /* Device time in ms of the stages of the last fmcw_run / fmcw_process_frames (CUDA events on the
  * handle's stream; synchronises): ms[0] frame chain, ms[1] compaction, ms[2] STFT plan + global max,

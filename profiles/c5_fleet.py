@@ -33,6 +33,7 @@ ap.add_argument("--radars", type=int, default=1024)
 ap.add_argument("--frames", type=int, default=500)
 ap.add_argument("--handles", type=int, default=8)
 ap.add_argument("--passes", type=int, default=3)
+ap.add_argument("--only", type=int, default=0, help="first N entries of the sweep only")
 a = ap.parse_args()
 world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
@@ -56,11 +57,14 @@ for r in mine:
     recs.append(iq)
 g.close()
 sweep = [(20, 19)] + [(w, int(w * ov)) for w in (32, 64, 128, 256) for ov in (0.5, 0.75, 0.9)]
+if a.only:
+    sweep = sweep[:a.only]
 rows = []
 for win, ov in sweep:
     cfg = fmcw_configurations(sx, window_length=win, overlap=ov)
     fleet = Fleet(cfg, calib, n_handles=a.handles, device=lr)
-    fleet.run(recs)                                         # warm-up: buffers, plans, graphs
+    for _ in range(3):                                      # warm-up: buffers, plans; the third pass records the run graphs
+        fleet.run(recs)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()

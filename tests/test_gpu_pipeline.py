@@ -291,22 +291,74 @@ def test_fleet_of_radars_equals_one_by_one():
     cfg, calib = cases[0]["cfg"], cases[0]["calib"]
     recs = [torch.from_numpy(c["iq"]).cuda() for c in cases]
     fleet = Fleet(cfg, calib, n_handles=3)
-    got = fleet.run(recs)
     h = FmcwCuda(cfg, calib)
-    for i, rec in enumerate(recs):
+    want = []
+    for rec in recs:
         out, inten = h.run(rec)
         info = h.info()
-        g = got[i]
-        assert g["info"]["n_detected"] == info["n_detected"] and g["info"]["nfft"] == info["nfft"]
-        assert g["info"]["pmax_raw"] == info["pmax_raw"] and g["ncol"] == info["ncol_local"]
-        for k in ("detected", "range_bin", "doppler_bin", "range_mag", "range_max_abs"):
-            assert torch.equal(g[k], out[k]), k
-        n = info["ncol_local"]
-        a, b = g["intensity"][:n], inten[:n]
-        assert torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
-    assert got[2]["info"]["n_detected"] == 0 and got[2]["ncol"] == 0
+        want.append(({k: v.clone() for k, v in out.items()}, inten[:info["ncol_local"]].clone(), info))
+    # passes 1-2 run launch by launch, pass 3 records every recording's run as one CUDA graph, passes 4-5 replay the graphs
+    for p in range(5):
+        for g in fleet._bufs.values():                         # results of the previous pass must not survive by accident
+            g[2].fill_(-1.0)
+        got = fleet.run(recs)
+        for i, (out, inten, info) in enumerate(want):
+            g = got[i]
+            assert g["info"]["n_detected"] == info["n_detected"] and g["info"]["nfft"] == info["nfft"], (p, i)
+            assert g["info"]["pmax_raw"] == info["pmax_raw"] and g["ncol"] == info["ncol_local"], (p, i)
+            assert g["info"]["n_frames"] == info["n_frames"] and g["info"]["L_local"] == info["L_local"]
+            for k in ("detected", "range_bin", "doppler_bin", "range_mag", "range_max_abs"):
+                assert torch.equal(g[k], out[k]), (p, i, k)
+            n = info["ncol_local"]
+            assert torch.equal(torch.nan_to_num(g["intensity"][:n], nan=7.0), torch.nan_to_num(inten, nan=7.0)), (p, i)
+        assert got[2]["info"]["n_detected"] == 0 and got[2]["ncol"] == 0
     h.close()
     fleet.close()
+
+
+def test_run_graph_option_replays_and_survives_buffer_growth():
+    """FMCW_OPT_RUN_GRAPH on one handle: the third run on a buffer set is recorded, later ones replay it; a bigger recording in
+    between moves the scratch buffers, which drops the recorded graphs instead of replaying stale addresses."""
+    import torch
+    from fmcw_radar_processing_b200 import _lib
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    small = H.make_case(n_frames=24, NTS=128, PN=64, seed=5)
+    big = H.make_case(n_frames=90, NTS=128, PN=64, seed=6)
+    cfg, calib = small["cfg"], small["calib"]
+    ref = FmcwCuda(cfg, calib)
+    iq_s, iq_b = torch.from_numpy(small["iq"]).cuda(), torch.from_numpy(big["iq"]).cuda()
+    out_s, inten_s = ref.run(iq_s)
+    n_s = ref.info()["ncol_local"]
+    want_s = inten_s[:n_s].clone()
+    out_b, inten_b = ref.run(iq_b)
+    n_b = ref.info()["ncol_local"]
+    want_b = inten_b[:n_b].clone()
+    h = FmcwCuda(cfg, calib)
+    h.set_option(_lib.OPT_RUN_GRAPH, 1)
+    o1 = h.alloc_frame_out(24, device=iq_s.device)
+    i1 = torch.empty((max(1, h.max_cols(24)), h.nq), dtype=torch.float32, device=iq_s.device)
+    o2 = h.alloc_frame_out(90, device=iq_s.device)
+    i2 = torch.empty((max(1, h.max_cols(90)), h.nq), dtype=torch.float32, device=iq_s.device)
+    for p in range(5):                                         # plain, plain, recorded, replayed, replayed
+        i1.fill_(-1.0)
+        h.run(iq_s, o1, i1)
+        assert h.info()["ncol_local"] == n_s
+        assert torch.equal(i1[:n_s], want_s), p
+        assert torch.equal(o1["range_bin"], out_s["range_bin"])
+    h.run(iq_b, o2, i2)                                        # grows xc / o_slow64 / ...: the small recording's graph is stale now
+    assert torch.equal(i2[:n_b], want_b)
+    for p in range(4):
+        i1.fill_(-1.0)
+        h.run(iq_s, o1, i1)
+        assert torch.equal(i1[:n_s], want_s), p
+        i2.fill_(-1.0)
+        h.run(iq_b, o2, i2)
+        assert h.info()["ncol_local"] == n_b
+        assert torch.equal(i2[:n_b], want_b), p
+    t = h.timings()                                            # replayed runs carry no stage events
+    assert t["chain_ms"] == 0.0 and t["stft_main_ms"] == 0.0
+    h.close()
+    ref.close()
 
 
 def test_all_rx_streams_match_the_oracle_per_antenna():

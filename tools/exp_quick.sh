@@ -1,5 +1,2 @@
-B="python bench.py --workload c2 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extra"
-for d in 0 2048 68 76; do
-  echo "== dbg $d"
-  FMCW_TC_PROF=1 FMCW_TC_DEBUG=$d timeout 120 $B 2>&1 | grep "PROF cta  77" | sort | uniq | awk '{k=$5 $6 $7; if (!(k in seen)) {seen[k]=1; print}}' | grep -v "lane [123]"
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python profiles/c5_fleet.py --radars 128 --handles 8 --only 4 --passes 5 2>&1 | python -c "import sys,json; d=json.load(sys.stdin); print([(r['window'], r['hop'], round(r['seconds_per_pass_max_over_ranks']*1e3,2)) for r in d['sweep']])"
