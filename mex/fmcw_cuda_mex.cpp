@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mex.h"
@@ -31,6 +32,7 @@ fmcw_config g_cfg;
 bool g_have_cfg = false;
 
 bool g_locked = false;
+std::vector<std::pair<int, int64_t>> g_opts;     // fmcw_cuda_mex('option', id, value): applied to every handle
 
 // Destroys the handle and releases the lock taken when it was created, so that `clear fmcw_cuda_mex` works again once no
 // handle is alive (one mexLock per live handle, never more: mexLock counts).
@@ -81,6 +83,24 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     char cmd[16] = {0};
     mxGetString(prhs[0], cmd, sizeof(cmd));
     if (std::strcmp(cmd, "release") == 0) { release_handle(); plhs[0] = mxCreateDoubleScalar(0.0); break; }   // fmcw_cuda_mex('release'): frees the GPU state, unlocks the MEX file
+    if (std::strcmp(cmd, "option") == 0) {
+      // fmcw_cuda_mex('option', id, value): fmcw_set_option on the current handle and on every handle created later
+      // (id 2 = FMCW_OPT_STFT_PRECISION: 0 tensor-core kernel, 1 float64 kernel; see include/fmcw_cuda.h)
+      if (nrhs != 3 || !mxIsNumeric(prhs[1]) || !mxIsNumeric(prhs[2]) || mxGetNumberOfElements(prhs[1]) != 1 || mxGetNumberOfElements(prhs[2]) != 1) {
+        err_id = "fmcw:usage"; err_msg = "fmcw_cuda_mex('option', id, value)"; break;
+      }
+      const int id = (int)mxGetScalar(prhs[1]);
+      const int64_t value = (int64_t)mxGetScalar(prhs[2]);
+      if (g_handle) {
+        const fmcw_status st = fmcw_set_option(g_handle, id, value);
+        if (st != FMCW_OK) { err_id = "fmcw:option"; err_msg = fmcw_last_error(g_handle); break; }
+      }
+      bool found = false;
+      for (auto& o : g_opts) if (o.first == id) { o.second = value; found = true; }
+      if (!found) g_opts.push_back(std::make_pair(id, value));
+      plhs[0] = mxCreateDoubleScalar(0.0);
+      break;
+    }
     if (nrhs != 4 || !mxIsStruct(prhs[3])) { err_id = "fmcw:usage"; err_msg = "out = fmcw_cuda_mex(cmd, data, calib_data, cfg)"; break; }
     fmcw_config c;
     std::string missing;
@@ -91,6 +111,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       fmcw_status st = fmcw_create(&c, cal, cal ? (uint64_t)mxGetNumberOfElements(prhs[2]) : 0, 0, &g_handle);
       if (st != FMCW_OK) { err_id = "fmcw:create"; err_msg = fmcw_status_string(st); g_handle = nullptr; break; }
       g_cfg = c; g_have_cfg = true;
+      bool opt_ok = true;
+      for (const auto& o : g_opts) if (fmcw_set_option(g_handle, o.first, o.second) != FMCW_OK) opt_ok = false;
+      if (!opt_ok) { err_id = "fmcw:option"; err_msg = fmcw_last_error(g_handle); break; }
       if (!g_locked) { mexLock(); g_locked = true; }
       mexAtExit(at_exit);
     }

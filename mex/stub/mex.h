@@ -11,7 +11,7 @@ typedef enum { mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7, mxINT16_CLASS = 10, mxINT
 extern "C" {
 #endif
 bool mxIsChar(const mxArray*); bool mxIsStruct(const mxArray*); bool mxIsDouble(const mxArray*); bool mxIsSingle(const mxArray*);
-bool mxIsInt16(const mxArray*); bool mxIsEmpty(const mxArray*);
+bool mxIsInt16(const mxArray*); bool mxIsEmpty(const mxArray*); bool mxIsNumeric(const mxArray*);
 int mxGetString(const mxArray*, char*, mwSize);
 mxArray* mxGetField(const mxArray*, mwSize, const char*);
 void mxSetField(mxArray*, mwSize, const char*, mxArray*);

@@ -89,6 +89,24 @@ napi_value Destroy(napi_env env, napi_callback_info info) {
   return nullptr;
 }
 
+// setOption(handle, id, value): fmcw_set_option (id 2 = FMCW_OPT_STFT_PRECISION: 0 tensor-core kernel, 1 float64 kernel)
+napi_value SetOption(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value argv[3];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  if (argc < 3) { napi_throw_error(env, "FMCW_USAGE", "setOption(handle, id, value)"); return nullptr; }
+  Wrapped* w = nullptr;
+  if (napi_get_value_external(env, argv[0], (void**)&w) != napi_ok || !w || !w->h) {
+    napi_throw_error(env, "FMCW_HANDLE", "setOption: not a live handle"); return nullptr;
+  }
+  int32_t id = 0; int64_t value = 0;
+  if (napi_get_value_int32(env, argv[1], &id) != napi_ok || napi_get_value_int64(env, argv[2], &value) != napi_ok) {
+    napi_throw_error(env, "FMCW_TYPE", "setOption: id and value must be numbers"); return nullptr;
+  }
+  const fmcw_status st = fmcw_set_option(w->h, id, value);
+  if (st != FMCW_OK) { napi_throw_error(env, "FMCW_OPTION", fmcw_last_error(w->h)); return nullptr; }
+  return nullptr;
+}
+
 void Execute(napi_env, void* data) {   // libuv pool thread: no N-API calls here
   Job* j = (Job*)data;
   const fmcw_config& c = j->cfg;
@@ -190,6 +208,7 @@ napi_value Init(napi_env env, napi_value exports) {
   napi_create_function(env, "create", NAPI_AUTO_LENGTH, Create, nullptr, &f); napi_set_named_property(env, exports, "create", f);
   napi_create_function(env, "destroy", NAPI_AUTO_LENGTH, Destroy, nullptr, &f); napi_set_named_property(env, exports, "destroy", f);
   napi_create_function(env, "run", NAPI_AUTO_LENGTH, Run, nullptr, &f); napi_set_named_property(env, exports, "run", f);
+  napi_create_function(env, "setOption", NAPI_AUTO_LENGTH, SetOption, nullptr, &f); napi_set_named_property(env, exports, "setOption", f);
   return exports;
 }
 

@@ -22,6 +22,8 @@ napi_status napi_has_named_property(napi_env, napi_value, const char*, bool*);
 napi_status napi_get_named_property(napi_env, napi_value, const char*, napi_value*);
 napi_status napi_set_named_property(napi_env, napi_value, const char*, napi_value);
 napi_status napi_get_value_double(napi_env, napi_value, double*);
+napi_status napi_get_value_int32(napi_env, napi_value, int32_t*);
+napi_status napi_get_value_int64(napi_env, napi_value, int64_t*);
 napi_status napi_get_typedarray_info(napi_env, napi_value, napi_typedarray_type*, size_t*, void**, napi_value*, size_t*);
 napi_status napi_create_external(napi_env, void*, napi_finalize, void*, napi_value*);
 napi_status napi_get_value_external(napi_env, napi_value, void**);
