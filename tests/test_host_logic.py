@@ -146,3 +146,23 @@ def test_spectrogram_png_writer(tmp_path):
     assert tuple(px[-1, 0]) == (128, 0, 0)                      # 0 dB -> top of jet (dark red), bottom image row = lowest frequency
     assert tuple(px[0, 0]) == (0, 0, 128)                       # below clim -> bottom of jet (dark blue)
     assert px[h - 1 - 20, 0, 1] > 200                           # -20 dB = middle of the map: green channel saturated
+
+
+def test_device_info_records_decode_like_the_c_struct():
+    """fleet.py reads one fmcw_device_info per recording from a single device copy: the ctypes mirror has the C layout
+    (9 x u64, 2 x u32, f64, 2 x i32 = 96 bytes) and parse_device_infos walks consecutive records."""
+    import ctypes as C
+    from fmcw_radar_processing_b200 import _lib
+    from fmcw_radar_processing_b200.api import FmcwCuda
+    assert C.sizeof(_lib.fmcw_run_info) == 88 and C.sizeof(_lib.fmcw_device_info) == 96
+    recs = (_lib.fmcw_device_info * 3)()
+    for i, r in enumerate(recs):
+        r.info.n_frames = 500 + i; r.info.n_detected = 400 + i; r.info.L_local = (400 + i) * 64; r.info.nfft = 32768
+        r.info.ncol_local = (400 + i) * 64 - 19; r.info.pmax_raw = 1.5e9 * (i + 1); r.status = -4 * (i == 2)
+    raw = np.frombuffer(bytes(recs), dtype=np.uint8)
+    out = FmcwCuda.parse_device_infos(raw)
+    assert len(out) == 3
+    for i, (info, status) in enumerate(out):
+        assert info["n_frames"] == 500 + i and info["n_detected"] == 400 + i and info["nfft"] == 32768
+        assert info["ncol_local"] == (400 + i) * 64 - 19 and info["pmax_raw"] == 1.5e9 * (i + 1)
+        assert status == (-4 if i == 2 else 0)
