@@ -20,11 +20,14 @@
 //   * A tiles are written to shared memory by a dedicated builder warp, one tile ahead (K-major, no swizzle, core
 //     matrices of 8 rows x 16 bytes); B tiles (planned once on the device) arrive by 1-D bulk copy (cp.async.bulk) on an
 //     mbarrier; tcgen05.commit signals the epilogue, which reads the accumulators with tcgen05.ld, takes
-//     |S|^2 -> lg2, interpolates, scales to dB and writes the spectrogram.
-// One CTA per SM (608 threads): warps 0-15 epilogue (lane quarter = warp & 3; the four warps of a quarter each
-// take 16 queries of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer, warp 18 A-tile builder.  TMEM (512 columns), the A
-// tiles, the B tiles and the output staging rows are double buffered: the MMAs of chunk c+1 and the stores of
-// chunk c-1 overlap the lg2 phase of chunk c.
+//     |S|^2 -> lg2, interpolates, scales to dB and stages the spectrogram rows in shared memory.
+// One CTA per SM (736 threads): warps 0-15 epilogue (lane quarter = warp & 3; the four warps of a quarter each take 16 queries
+// of every chunk), warp 16 MMA issuer, warp 17 bulk-copy producer, warp 18 A-tile builder, warps 19-22 TMA-store issuers (one
+// per quarter: 32 columns x 64 queries leave as one 3-D cp.async.bulk.tensor store of two 128-byte-swizzled boxes).  TMEM (512
+// columns), the A tiles, the B tiles and the output staging boxes are double buffered: the MMAs of chunk c+1 and the stores of
+// chunk c-1 overlap the lg2 phase of chunk c.  Without a tensor map (run-time query count, frequency-major layout,
+// FMCW_TC_TMA=0) the epilogue warps flush the staged rows themselves (64-bit shared-memory loads, coalesced global stores).
+// What bounds the kernel, measured: profiles/stft_tc_bounds_r2.txt (FMCW_TC_DEBUG / FMCW_TC_PROF below are its instruments).
 #include <cstdio>
 #include <cstdlib>
 
