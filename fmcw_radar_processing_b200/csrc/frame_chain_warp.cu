@@ -111,6 +111,10 @@ __device__ __forceinline__ void dft16(cx2 (&v)[16]) {
 
 constexpr int WF_XROW = 17;                      // float4 stride between rows of the in-warp transpose
 constexpr int WF_XHALF = 16 * WF_XROW;           // float4 per half-warp slice (two chirps)
+#ifndef FMCW_WF_SOA
+#define FMCW_WF_SOA 1
+#endif
+constexpr bool WF_SOA = FMCW_WF_SOA != 0;        // transpose through two float2 planes instead of one float4 plane
 
 struct WarpSmem {                                // byte offsets inside the dynamic shared memory
   int tw, wg, wh, dtw, dwin, per_warp0, per_warp;
@@ -282,14 +286,27 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) frame_chain_warp_kernel(c
         v[k1].re = __ffma2_rn(a.im, neg2(s2), __fmul2_rn(a.re, c2));
         v[k1].im = __ffma2_rn(a.re, s2, __fmul2_rn(a.im, c2));
       }
+      if (WF_SOA) {
+        // Re pairs and Im pairs in two float2 planes (row stride 17): 64-bit stores and loads straight from / into the register
+        // pairs the packed arithmetic uses, conflict-free both ways (a 128-bit store needs four consecutive registers, which
+        // cost ~4 MOVs apiece at this register pressure)
+        float2* xre = reinterpret_cast<float2*>(xch);
+        float2* xim = xre + WF_XHALF;
 #pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) xch[k1 * WF_XROW + s] = make_float4(v[k1].re.x, v[k1].re.y, v[k1].im.x, v[k1].im.y);
-      __syncwarp();
+        for (int k1 = 0; k1 < 16; ++k1) { xre[k1 * WF_XROW + s] = v[k1].re; xim[k1 * WF_XROW + s] = v[k1].im; }
+        __syncwarp();
 #pragma unroll
-      for (int n2 = 0; n2 < 16; ++n2) {
-        const float4 t = xch[s * WF_XROW + n2];
-        v[n2].re = make_float2(t.x, t.y);
-        v[n2].im = make_float2(t.z, t.w);
+        for (int n2 = 0; n2 < 16; ++n2) { v[n2].re = xre[s * WF_XROW + n2]; v[n2].im = xim[s * WF_XROW + n2]; }
+      } else {
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) xch[k1 * WF_XROW + s] = make_float4(v[k1].re.x, v[k1].re.y, v[k1].im.x, v[k1].im.y);
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+          const float4 t = xch[s * WF_XROW + n2];
+          v[n2].re = make_float2(t.x, t.y);
+          v[n2].im = make_float2(t.z, t.w);
+        }
       }
       __syncwarp();
       if (PF) load_quad(q + 1);   // in flight during the second radix-16 stage and the next unpack
