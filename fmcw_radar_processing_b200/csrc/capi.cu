@@ -815,7 +815,7 @@ fmcw_status fmcw_run(fmcw_handle* h, const int16_t* iq, uint64_t n_frames, const
     if (all_dev) {
       for (auto& e : h->run_graphs)
         if (std::memcmp(&e.key, &key, sizeof(key)) == 0) { rg = &e; break; }
-      if (!rg && h->run_graphs.size() < 4096) {
+      if (!rg && h->run_graphs.size() < 256) {        // (linear search; more buffer sets than this per handle simply run plainly)
         h->run_graphs.push_back(fmcw_handle::RunGraph{key, nullptr, 0, 0});
         rg = &h->run_graphs.back();
       }

@@ -715,7 +715,7 @@ cudaError_t launch_stft_tc_main(const StftTables& t, const StftGeom& g, const si
   if (layout != 0) return launch_tc<1, 0>(FMCW_TC_ARGS);
   // the fast path stores 64-bit pairs: 1,024 queries and an 8-byte aligned spectrogram
   static const int use_tma = env_int("FMCW_TC_TMA", 1);
-  if (use_tma && g.nq == 1024 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+  if (use_tma && g.nq == 1024 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && capacity_cols < (1ull << 31)) {   // (tensor coordinates are int32)
     // TMA-store epilogue: the staged rows leave through the async proxy (no LDS / STG on the LSU pipe).  Rows between the
     // column count and capacity_cols that share the last tile are overwritten (with copies of the last column).
     CUtensorMap map;

@@ -155,7 +155,8 @@ FMCW_API fmcw_status fmcw_synchronize(fmcw_handle* h);
  * FMCW_OPT_RUN_GRAPH = 3: 1 = fmcw_run calls whose buffers are all device memory are recorded as ONE CUDA graph per set of
  *   buffers (input, outputs, info target) the third time the set is seen and replayed from then on.  For fleets of small
  *   recordings (BASELINE C5): a 500-frame recording is about 12 kernel launches and the GPU's launch rate, not its work, bounds
- *   the pass.  Results are identical; fmcw_get_timings reports 0 for replayed runs.
+ *   the pass.  Results are identical; fmcw_get_timings reports 0 for replayed runs; a handle keeps at most 256 buffer sets and
+ *   drops every recorded graph when one of its scratch buffers has to grow.
  *
  * FMCW_OPT_STFT_TILES_PER_CTA = 4: n > 1 = the persistent tensor-core STFT kernel is launched with one CTA per n tiles (128 columns)
  *   of the output buffer's capacity instead of one per SM when that is fewer: the kernels of several small recordings on
