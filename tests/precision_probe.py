@@ -1,5 +1,5 @@
 """Precision probe (not a test): prints parity metrics of the CUDA path against the float64 oracle, including the
-spectrogram error by level band quoted in DESIGN.md.  python profiles/precision_probe.py > profiles/precision_<round>.txt"""
+spectrogram error by level band quoted in DESIGN.md.  python tests/precision_probe.py > profiles/precision_<round>.txt"""
 import sys, time
 import numpy as np
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
