@@ -27,11 +27,21 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
 
 
+def test_every_entry_point_is_documented_in_integration_md():
+    """INTEGRATION.md names, for every C entry point, the reference lines it replaces (or says the reference has none)."""
+    hdr = open(os.path.join(ROOT, "include", "fmcw_cuda.h")).read()
+    declared = set(re.findall(r"FMCW_API\s+[\w\s\*]+?\b(fmcw_\w+)\s*\(", hdr))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(n for n in declared if n not in doc)
+    assert not missing, missing
+
+
 def test_struct_layout_matches_header(lib):
     assert C.sizeof(lib.fmcw_config) == 14 * 4 + 18 * 8
     assert C.sizeof(lib.fmcw_frame_out) == 7 * 8
     assert C.sizeof(lib.fmcw_stft_out) == 32
     assert C.sizeof(lib.fmcw_run_info) == 9 * 8 + 8 + 8
+    assert C.sizeof(lib.fmcw_device_info) == C.sizeof(lib.fmcw_run_info) + 8
     assert lib.load().fmcw_version().startswith(b"libfmcw_cuda")
 
 
